@@ -1,0 +1,345 @@
+// Path D — non-causal multi-head attention forward, head_dim 128, on tcgen05 / TMEM.
+//   O = softmax(Q K^T * scale) V        (reference: cosmos_predict1/diffusion/module/attention.py
+//   :282-297 `cal_attn` -> transformer_engine DotProductAttention(sbhd, no_mask, dropout 0);
+//   self-attention Lq = Lk = 56 320, cross-attention Lk = 512)
+//
+// Layouts (all bf16, produced by the projection GEMMs of gemm_tcgen05.cu):
+//   Q  [Lq, heads*128]  token-major          K [Lk, heads*128] token-major
+//   Vt [chunks][heads*128][chunk_len]        (V transposed, keys contiguous -> K-major B operand;
+//                                             `chunks` = context-parallel ranks after the KV
+//                                             all-gather, 1 otherwise)
+//   O  [Lq, heads*128]
+//
+// One CTA = 256 query rows (two 128-row tiles A/B) of one head, 320 threads:
+//   warps 0-3  softmax of tile A   (thread = one query row; S row read from TMEM into registers)
+//   warps 4-7  softmax of tile B
+//   warp  8    TMA producer: Q once, then K_j / V_j through a 4-slot ring of 32 KB tiles
+//   warp  9    TMEM allocator + single-thread MMA issuer
+// TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,384) O_B [384,512); P (bf16) overwrites
+// the first 64 columns of its S tile and feeds the P·V MMA straight from TMEM.
+// MMA order per KV step j:  PV_A(j) ; S_A(j+1) ; PV_B(j) ; S_B(j+1)  — the S MMA of one tile and
+// the whole PV/S pair of the other overlap with that tile's softmax.
+// Online softmax keeps a lazily updated reference max: O / row-sum are only rescaled when the row
+// max grew by more than 2^8, so the TMEM read-modify-write of O is rare after the first tiles.
+#include "kernels.h"
+
+namespace g3c {
+
+constexpr int ATT_THREADS = 320;
+constexpr int ATT_TILE = 128;             // rows per Q tile, keys per KV tile, head dim
+constexpr int ATT_HALF_BYTES = 128 * 128; // one 64-column half of a 128x128 bf16 tile
+constexpr int ATT_TILE_BYTES = 2 * ATT_HALF_BYTES;
+constexpr int ATT_SLOTS = 4;
+constexpr int ATT_SMEM = 2 * ATT_TILE_BYTES + ATT_SLOTS * ATT_TILE_BYTES + 256 + 1024;
+
+struct AttnParams {
+  int Lq, Lk, heads;
+  int ldo;
+  int vt_chunk_len;
+  __nv_bfloat16* O;
+  float scale_log2;  // softmax scale * log2(e)
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+    k_attn_fwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_q = smem;                        // [2 tiles][2 halves][128 x 128 B]
+  uint8_t* smem_kv = smem + 2 * ATT_TILE_BYTES;  // [slots][2 halves][128 x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + ATT_SLOTS * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;                        // [1]
+  uint64_t* kv_full = bars + 1;                   // [slots]
+  uint64_t* kv_empty = bars + 1 + ATT_SLOTS;      // [slots]
+  uint64_t* s_full = bars + 1 + 2 * ATT_SLOTS;    // [2]
+  uint64_t* p_full = bars + 3 + 2 * ATT_SLOTS;    // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5 + 2 * ATT_SLOTS);
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * 2 * ATT_TILE;
+  const int n_kv = p.Lk / ATT_TILE;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < ATT_SLOTS; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          tma_load_2d(smem_q + t * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmQ, q_full,
+                      head * 128 + h * 64, q0 + t * ATT_TILE);
+      uint32_t slot = 0, phase = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        const int kv0 = j * ATT_TILE;
+        // K_j
+        mbar_wait(&kv_empty[slot], phase ^ 1);
+        mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          tma_load_2d(smem_kv + slot * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmK, &kv_full[slot],
+                      head * 128 + h * 64, kv0);
+        if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; }
+        // V_j  (transposed: rows = head dim, columns = keys)
+        mbar_wait(&kv_empty[slot], phase ^ 1);
+        mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
+        const int chunk = kv0 / p.vt_chunk_len;
+        const int koff = kv0 - chunk * p.vt_chunk_len;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(smem_kv + slot * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmV, &kv_full[slot],
+                      koff + h * 64, head * 128, chunk);
+        if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+      const uint32_t tS[2] = {tmem_base, tmem_base + 128};
+      const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
+      uint32_t slot = 0, phase = 0;
+      auto advance = [&]() { if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; } };
+      auto mma_s = [&](int t, uint32_t kslot) {
+        // S_t = Q_t K^T : 8 k-steps over the head dimension
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t half = k >> 2, off = (k & 3) * 32;
+          uint64_t da = make_sdesc_sw128(smem_u32(smem_q + t * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
+          uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + kslot * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
+          umma_ss(tS[t], sdesc_advance(da, off), sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
+        }
+      };
+      auto mma_pv = [&](int t, uint32_t vslot, bool first) {
+        // O_t += P_t V : 8 k-steps over the 128 keys; A = P from TMEM (bf16 pairs per column)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t half = k >> 2, off = (k & 3) * 32;
+          uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + vslot * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
+          umma_ts(tO[t], tS[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
+        }
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[slot], phase);
+      tc_fence_after();
+      uint32_t kslot = slot;
+      advance();
+      mma_s(0, kslot);
+      umma_commit(&s_full[0]);
+      mma_s(1, kslot);
+      umma_commit(&s_full[1]);
+      umma_commit(&kv_empty[kslot]);
+      for (int j = 0; j < n_kv; ++j) {
+        const bool more = j + 1 < n_kv;
+        mbar_wait(&kv_full[slot], phase);  // V_j
+        const uint32_t vslot = slot;
+        advance();
+        // ---- tile A
+        mbar_wait(&p_full[0], j & 1);
+        tc_fence_after();
+        mma_pv(0, vslot, j == 0);
+        if (more) {
+          mbar_wait(&kv_full[slot], phase);  // K_{j+1}
+          tc_fence_after();
+          kslot = slot;
+          advance();
+          mma_s(0, kslot);
+        }
+        umma_commit(&s_full[0]);
+        // ---- tile B
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        mma_pv(1, vslot, j == 0);
+        umma_commit(&kv_empty[vslot]);
+        if (more) {
+          mma_s(1, kslot);
+          umma_commit(&s_full[1]);
+          umma_commit(&kv_empty[kslot]);
+        } else {
+          umma_commit(&s_full[1]);
+        }
+      }
+    }
+  } else {
+    // ===== softmax warpgroups (warps 0-3: tile A, warps 4-7: tile B) =====
+    const int t = warp >> 2;
+    const uint32_t lane_base = ((warp & 3u) * 32u) << 16;
+    const uint32_t tS = tmem_base + lane_base + t * 128;
+    const uint32_t tO = tmem_base + lane_base + 256 + t * 128;
+    const float c = p.scale_log2;
+    float m_used = 0.0f;  // reference max (raw score units) the stored exponentials are relative to
+    float l = 0.0f;       // running row sum (relative to m_used)
+    uint32_t sphase = 0;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[t], sphase);
+      sphase ^= 1;
+      tc_fence_after();
+      uint32_t s[128];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) tmem_ld32(tS + cc * 32, s + cc * 32);
+      tc_wait_ld();
+      float mx = __uint_as_float(s[0]);
+#pragma unroll
+      for (int i = 1; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(s[i]));
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const bool grow = (mx - m_used) * c > 8.0f;
+        if (__any_sync(0xffffffffu, grow)) {
+          // s_full(j) was committed after PV(j-1): O already holds every earlier contribution.
+          const float m_new = fmaxf(m_used, mx);
+          const float alpha = ex2_approx((m_used - m_new) * c);
+          m_used = m_new;
+          l *= alpha;
+#pragma unroll 1
+          for (int cc = 0; cc < 4; ++cc) {
+            uint32_t o[32];
+            tmem_ld32(tO + cc * 32, o);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tO + cc * 32, o);
+          }
+          tc_wait_st();
+        }
+      }
+      const float neg = -m_used * c;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float a = ex2_approx(fmaf(__uint_as_float(s[hh * 64 + 2 * i]), c, neg));
+          float b = ex2_approx(fmaf(__uint_as_float(s[hh * 64 + 2 * i + 1]), c, neg));
+          l += a + b;
+          pk[i] = pack_bf16x2(a, b);
+        }
+        tmem_st32(tS + hh * 32, pk);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[t]);
+    }
+    // final: PV(n_kv-1) complete
+    mbar_wait(&s_full[t], sphase);
+    tc_fence_after();
+    const int row = q0 + t * ATT_TILE + (warp & 3) * 32 + lane;
+    const float inv = 1.0f / l;
+    __nv_bfloat16* optr = p.O + (size_t)row * p.ldo + head * 128;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      uint32_t o[32];
+      tmem_ld32(tO + cc * 32, o);
+      tc_wait_ld();
+      if (row < p.Lq) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 q;
+          q.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+          q.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+          q.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+          q.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+          reinterpret_cast<uint4*>(optr + cc * 32)[i] = q;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int attn_fwd(const void* q, const void* k, const void* vt, void* o, int Lq, int Lk, int heads,
+             int ldq, int ldk, int ldo, int vt_chunk_len, float scale, cudaStream_t st) {
+  G3C_REQUIRE(q && k && vt && o, "attn: null operand");
+  G3C_REQUIRE(Lq > 0 && Lk > 0 && heads > 0, "attn: bad sizes");
+  G3C_REQUIRE(Lk % ATT_TILE == 0, "attn: Lk=%d must be a multiple of 128", Lk);
+  if (vt_chunk_len <= 0) vt_chunk_len = Lk;
+  G3C_REQUIRE(Lk % vt_chunk_len == 0 && vt_chunk_len % ATT_TILE == 0,
+              "attn: vt_chunk_len=%d must divide Lk=%d and be a multiple of 128", vt_chunk_len, Lk);
+  G3C_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldo % 8 == 0 && ldq >= heads * 128 &&
+                  ldk >= heads * 128 && ldo >= heads * 128,
+              "attn: leading dimensions must be >= heads*128 and multiples of 8");
+  G3C_REQUIRE((reinterpret_cast<uintptr_t>(o) & 15) == 0, "attn: O must be 16-byte aligned");
+  CUtensorMap tmQ, tmK, tmV;
+  {
+    uint64_t dims[2] = {(uint64_t)heads * 128, (uint64_t)Lq}, str[1] = {(uint64_t)ldq * 2};
+    uint32_t box[2] = {64, 128};
+    int rc = make_tmap_bf16_sw128(&tmQ, q, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)heads * 128, (uint64_t)Lk}, str[1] = {(uint64_t)ldk * 2};
+    uint32_t box[2] = {64, 128};
+    int rc = make_tmap_bf16_sw128(&tmK, k, 2, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    const int chunks = Lk / vt_chunk_len;
+    uint64_t dims[3] = {(uint64_t)vt_chunk_len, (uint64_t)heads * 128, (uint64_t)chunks};
+    uint64_t str[2] = {(uint64_t)vt_chunk_len * 2, (uint64_t)vt_chunk_len * 2 * heads * 128};
+    uint32_t box[3] = {64, 128, 1};
+    int rc = make_tmap_bf16_sw128(&tmV, vt, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  static bool configured = false;
+  if (!configured) {
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    configured = true;
+  }
+  AttnParams p;
+  p.Lq = Lq;
+  p.Lk = Lk;
+  p.heads = heads;
+  p.ldo = ldo;
+  p.vt_chunk_len = vt_chunk_len;
+  p.O = reinterpret_cast<__nv_bfloat16*>(o);
+  p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((Lq + 2 * ATT_TILE - 1) / (2 * ATT_TILE), heads);
+  k_attn_fwd<<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+  G3C_CUDA(cudaGetLastError());
+  return G3C_OK;
+}
+
+}  // namespace g3c
+
+extern "C" int g3c_attn_fwd(const void* q, const void* k, const void* vt, void* o, int Lq, int Lk,
+                            int heads, int ldq, int ldk, int ldo, int vt_chunk_len, float scale,
+                            void* stream) {
+  return g3c::attn_fwd(q, k, vt, o, Lq, Lk, heads, ldq, ldk, ldo, vt_chunk_len, scale,
+                       (cudaStream_t)stream);
+}

@@ -1,0 +1,530 @@
+// Path D — the DiT forward and the denoise-step loop body as a native engine.
+//
+// Mirrors VideoExtendGeneralDIT.forward (reference: cosmos_predict1/diffusion/networks/
+// general_dit_video_conditioned.py:58-217, general_dit.py:272-358,439-522, module/blocks.py:419-475,
+// 537-558) for B = 1 and the FA-CA-MLP block layout, and the loop body of
+// DiffusionV2WModel.generate_samples_from_batch (model/model_v2w.py:130-149).
+//
+// Data layout in HBM (L = T_local*Hp*Wp tokens of this rank, D = model_channels):
+//   x      f32  [L, D]        residual stream (kept fp32; the reference keeps bf16)
+//   xn     bf16 [L, D]        LN-modulated activations = GEMM A operand
+//   q      bf16 [L, D]        k_all bf16 [cp*L, D]      vt_all bf16 [cp][D][L]  (V transposed)
+//   att    bf16 [L, D]        hid  bf16 [L, ffn]
+//   pos    bf16 [L, D]        per-block absolute position embedding (precomputed per shape)
+//   rope   f32  [L, 128]      cos|sin table (precomputed per shape)
+// Context parallelism: tokens are split contiguously along latent T (module/parallel.py:44-53);
+// per self-attention layer K and V^T of every rank are all-gathered in place (one ncclAllGather
+// each, same result as the reference's TE ring: general_dit.py:524-543).
+#include <dlfcn.h>
+
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "kernels.h"
+
+namespace g3c {
+
+// ---- NCCL, loaded at run time (the process normally already holds torch's libnccl.so.2) --------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+static NcclApi& nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      api.GetUniqueId = (int (*)(ncclUniqueId*))dlsym(h, "ncclGetUniqueId");
+      api.CommInitRank = (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+      api.CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
+      api.AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
+      api.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+      api.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+      api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather &&
+               api.GroupStart && api.GroupEnd;
+    }
+  }
+  return api;
+}
+constexpr int kNcclBfloat16 = 9;
+#define G3C_NCCL(x)                                                                      \
+  do {                                                                                   \
+    int _r = (x);                                                                        \
+    if (_r != 0) {                                                                       \
+      set_error("NCCL error %d (%s) in `%s`", _r,                                        \
+                nccl().GetErrorString ? nccl().GetErrorString(_r) : "?", #x);            \
+      return G3C_ENCCL;                                                                  \
+    }                                                                                    \
+  } while (0)
+
+struct WTensor {
+  const void* ptr = nullptr;
+  std::vector<int64_t> shape;
+  int dtype = 0;
+};
+
+struct SubBlock {
+  const __nv_bfloat16 *wq = nullptr, *wk = nullptr, *wv = nullptr, *wo = nullptr;  // attention
+  const float *gq = nullptr, *gk = nullptr;                                        // RMSNorm gamma (f32 copy)
+  const __nv_bfloat16 *w1 = nullptr, *w2 = nullptr;                                // MLP
+  const __nv_bfloat16 *ada1 = nullptr, *ada2 = nullptr;                            // adaLN-LoRA
+};
+
+}  // namespace g3c
+
+using namespace g3c;
+
+struct g3c_dit {
+  g3c_dit_config cfg;
+  std::unordered_map<std::string, WTensor> w;
+  bool resolved = false;
+  std::vector<std::array<SubBlock, 3>> blk;
+  const __nv_bfloat16 *w_t1 = nullptr, *w_t2 = nullptr, *w_final = nullptr, *f_ada1 = nullptr,
+                      *f_ada2 = nullptr, *affine_gamma = nullptr, *pos_t = nullptr, *pos_h = nullptr,
+                      *pos_w = nullptr;
+  __nv_bfloat16* w_patch_pad = nullptr;  // [D, Kpad] owned
+  float* gammas = nullptr;               // owned f32 copies of the RMSNorm weights
+  int Kpatch = 0, Kpad = 0;
+
+  // shape
+  int T = 0, Hl = 0, Wl = 0, Hp = 0, Wp = 0, L = 0, ctx_len = 0;
+  float fps = 24.f;
+  // cp
+  int cp_rank = 0, cp_size = 1;
+  ncclComm_t comm = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_kv = nullptr, ev_gathered = nullptr;
+  // workspace
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  float* x = nullptr;
+  __nv_bfloat16 *xn = nullptr, *q = nullptr, *k_all = nullptr, *vt_all = nullptr, *att = nullptr,
+                *hid = nullptr, *tok = nullptr, *pos = nullptr, *kc = nullptr, *vtc = nullptr;
+  float *rope = nullptr, *yfin = nullptr, *mods = nullptr, *modf = nullptr, *vec_s = nullptr,
+        *vec_emb = nullptr, *vec_h1 = nullptr, *vec_lora = nullptr, *vec_a = nullptr, *freqs = nullptr;
+  __nv_bfloat16 *lat_xtilde = nullptr, *lat_xin = nullptr, *lat_oc = nullptr, *lat_ou = nullptr;
+  bool tables_ready = false;
+  int launches = 0;
+};
+
+namespace g3c {
+
+static const WTensor* find(const g3c_dit* h, const std::string& name) {
+  auto it = h->w.find(name);
+  return it == h->w.end() ? nullptr : &it->second;
+}
+
+static int need_bf16(const g3c_dit* h, const std::string& name, std::initializer_list<int64_t> shape,
+                     const __nv_bfloat16** out) {
+  const WTensor* t = find(h, name);
+  if (!t) {
+    set_error("dit: weight `%s` was never loaded", name.c_str());
+    return G3C_ESTATE;
+  }
+  if (t->dtype != G3C_DTYPE_BF16) {
+    set_error("dit: weight `%s` must be bf16", name.c_str());
+    return G3C_EINVAL;
+  }
+  std::vector<int64_t> want(shape);
+  if (t->shape != want) {
+    std::string got, exp;
+    for (auto v : t->shape) got += std::to_string(v) + ",";
+    for (auto v : want) exp += std::to_string(v) + ",";
+    set_error("dit: weight `%s` has shape [%s] expected [%s]", name.c_str(), got.c_str(), exp.c_str());
+    return G3C_EINVAL;
+  }
+  *out = reinterpret_cast<const __nv_bfloat16*>(t->ptr);
+  return G3C_OK;
+}
+
+#define TRY(x)            \
+  do {                    \
+    int _rc = (x);        \
+    if (_rc) return _rc;  \
+  } while (0)
+
+static int resolve(g3c_dit* h, cudaStream_t st) {
+  if (h->resolved) return G3C_OK;
+  const g3c_dit_config& c = h->cfg;
+  const int64_t D = c.model_channels, R = c.adaln_lora_dim, F = c.ffn_dim, C = c.context_dim;
+  h->Kpatch = (c.in_channels + (c.concat_padding_mask ? 1 : 0)) * 4;
+  h->Kpad = (h->Kpatch + 63) / 64 * 64;
+  const __nv_bfloat16* wpe = nullptr;
+  TRY(need_bf16(h, "x_embedder.proj.1.weight", {D, h->Kpatch}, &wpe));
+  if (!h->w_patch_pad) G3C_CUDA(cudaMalloc(&h->w_patch_pad, (size_t)D * h->Kpad * 2));
+  G3C_CUDA(cudaMemsetAsync(h->w_patch_pad, 0, (size_t)D * h->Kpad * 2, st));
+  G3C_CUDA(cudaMemcpy2DAsync(h->w_patch_pad, (size_t)h->Kpad * 2, wpe, (size_t)h->Kpatch * 2,
+                             (size_t)h->Kpatch * 2, D, cudaMemcpyDeviceToDevice, st));
+  TRY(need_bf16(h, "extra_pos_embedder.pos_emb_t", {c.max_frames, D}, &h->pos_t));
+  TRY(need_bf16(h, "extra_pos_embedder.pos_emb_h", {c.max_h, D}, &h->pos_h));
+  TRY(need_bf16(h, "extra_pos_embedder.pos_emb_w", {c.max_w, D}, &h->pos_w));
+  TRY(need_bf16(h, "t_embedder.1.linear_1.weight", {D, D}, &h->w_t1));
+  TRY(need_bf16(h, "t_embedder.1.linear_2.weight", {3 * D, D}, &h->w_t2));
+  TRY(need_bf16(h, "affline_norm.weight", {D}, &h->affine_gamma));
+  TRY(need_bf16(h, "final_layer.linear.weight", {(int64_t)c.out_channels * 4, D}, &h->w_final));
+  TRY(need_bf16(h, "final_layer.adaLN_modulation.1.weight", {R, D}, &h->f_ada1));
+  TRY(need_bf16(h, "final_layer.adaLN_modulation.2.weight", {2 * D, R}, &h->f_ada2));
+  h->blk.resize(c.num_blocks);
+  if (!h->gammas) G3C_CUDA(cudaMalloc(&h->gammas, sizeof(float) * 128 * 4 * c.num_blocks));
+  for (int i = 0; i < c.num_blocks; ++i) {
+    for (int j = 0; j < 3; ++j) {
+      SubBlock& s = h->blk[i][j];
+      std::string p = "blocks.block" + std::to_string(i) + ".blocks." + std::to_string(j) + ".";
+      TRY(need_bf16(h, p + "adaLN_modulation.1.weight", {R, D}, &s.ada1));
+      TRY(need_bf16(h, p + "adaLN_modulation.2.weight", {3 * D, R}, &s.ada2));
+      if (j < 2) {
+        const int64_t kin = j == 0 ? D : C;
+        TRY(need_bf16(h, p + "block.attn.to_q.0.weight", {D, D}, &s.wq));
+        TRY(need_bf16(h, p + "block.attn.to_k.0.weight", {D, kin}, &s.wk));
+        TRY(need_bf16(h, p + "block.attn.to_v.0.weight", {D, kin}, &s.wv));
+        TRY(need_bf16(h, p + "block.attn.to_out.0.weight", {D, D}, &s.wo));
+        const __nv_bfloat16 *gq = nullptr, *gk = nullptr;
+        TRY(need_bf16(h, p + "block.attn.to_q.1.weight", {128}, &gq));
+        TRY(need_bf16(h, p + "block.attn.to_k.1.weight", {128}, &gk));
+        float* dst = h->gammas + (size_t)(i * 4 + j * 2) * 128;
+        TRY(bf16_to_f32(gq, dst, 128, st));
+        TRY(bf16_to_f32(gk, dst + 128, 128, st));
+        s.gq = dst;
+        s.gk = dst + 128;
+      } else {
+        TRY(need_bf16(h, p + "block.layer1.weight", {F, D}, &s.w1));
+        TRY(need_bf16(h, p + "block.layer2.weight", {D, F}, &s.w2));
+      }
+    }
+  }
+  h->resolved = true;
+  return G3C_OK;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int build_tables(g3c_dit* h, cudaStream_t st) {
+  if (h->tables_ready) return G3C_OK;
+  const g3c_dit_config& c = h->cfg;
+  // RoPE frequencies — reference: position_embedding.py:106-160 (head_dim 128 -> 44 | 42 | 42)
+  const int dim = 128, dim_h = dim / 6 * 2, dim_w = dim_h, dim_t = dim - 2 * dim_h;
+  const int nt = dim_t / 2, nh = dim_h / 2, nw = dim_w / 2;
+  std::vector<float> fr(64);
+  auto ntk = [](float ratio, int d) { return powf(ratio, (float)d / (float)(d - 2)); };
+  const float th_h = 10000.0f * ntk(c.rope_h_ratio, dim_h), th_w = 10000.0f * ntk(c.rope_w_ratio, dim_w),
+              th_t = 10000.0f * ntk(c.rope_t_ratio, dim_t);
+  for (int j = 0; j < nt; ++j) fr[j] = 1.0f / powf(th_t, (float)(2 * j) / (float)dim_t);
+  for (int j = 0; j < nh; ++j) fr[nt + j] = 1.0f / powf(th_h, (float)(2 * j) / (float)dim_h);
+  for (int j = 0; j < nw; ++j) fr[nt + nh + j] = 1.0f / powf(th_w, (float)(2 * j) / (float)dim_w);
+  G3C_CUDA(cudaMemcpyAsync(h->freqs, fr.data(), 64 * sizeof(float), cudaMemcpyHostToDevice, st));
+  G3C_CUDA(cudaStreamSynchronize(st));  // fr is a stack-lifetime host buffer
+  const int t0 = h->cp_rank * h->T;
+  // seq[:T] / fps * base_fps  (position_embedding.py:163)
+  const float t_scale = (1.0f / h->fps) * (float)c.base_fps;
+  TRY(rope_table(h->freqs, nt, nh, nw, t0, t_scale, h->T, h->Hp, h->Wp, h->rope, st));
+  TRY(abs_pos(h->pos_t, h->pos_h, h->pos_w, t0, h->T, h->Hp, h->Wp, c.model_channels, h->pos, st));
+  h->tables_ready = true;
+  return G3C_OK;
+}
+
+static int forward(g3c_dit* h, const void* x_in, const void* cond_mask, const void* cond_pose,
+                   const void* padding_mask, float timestep, const void* ctx, void* out,
+                   cudaStream_t st) {
+  G3C_REQUIRE(h && x_in && cond_mask && ctx && out, "dit_forward: null argument");
+  G3C_REQUIRE(h->L > 0, "dit_forward: g3c_dit_set_shape was not called");
+  TRY(resolve(h, st));
+  TRY(build_tables(h, st));
+  const g3c_dit_config& c = h->cfg;
+  const int D = c.model_channels, R = c.adaln_lora_dim, F = c.ffn_dim, L = h->L, heads = c.num_heads;
+  const int Lk_all = L * h->cp_size;
+  const float attn_scale = 1.0f / sqrtf(128.0f);
+  int n = 0;
+
+  // ---- input assembly + patch embedding (general_dit_video_conditioned.py:112-118,
+  //      general_dit.py:304-311, blocks.py:153-163)
+  PatchSrc src;
+  src.ptr[0] = (const __nv_bfloat16*)x_in;        src.nch[0] = 16;                      src.per_frame[0] = 1;
+  src.ptr[1] = (const __nv_bfloat16*)cond_mask;   src.nch[1] = 1;                       src.per_frame[1] = 1;
+  src.ptr[2] = (const __nv_bfloat16*)cond_pose;   src.nch[2] = c.in_channels - 17;      src.per_frame[2] = 1;
+  src.ptr[3] = (const __nv_bfloat16*)padding_mask; src.nch[3] = c.concat_padding_mask ? 1 : 0; src.per_frame[3] = 0;
+  TRY(patchify(src, h->T, h->Hp, h->Wp, h->Kpad, h->tok, st)); ++n;
+  TRY(gemm_bf16(h->tok, h->w_patch_pad, h->x, L, D, h->Kpad, h->Kpad, h->Kpad, D, G3C_EPI_F32, nullptr, 0, st)); ++n;
+
+  // ---- timestep embedding + all adaLN-LoRA modulation vectors (blocks.py:38-80, :442-445;
+  //      general_dit.py:405).  They depend on t only.
+  TRY(timestep_embed(timestep, D, h->affine_gamma, 1e-6f, h->vec_s, h->vec_emb, st)); ++n;
+  TRY(gemv(h->w_t1, h->vec_s, nullptr, h->vec_h1, D, D, 0, 0, st)); ++n;
+  TRY(gemv(h->w_t2, h->vec_h1, nullptr, h->vec_lora, 3 * D, D, 1, 0, st)); ++n;
+  for (int i = 0; i < c.num_blocks; ++i)
+    for (int j = 0; j < 3; ++j) {
+      const SubBlock& s = h->blk[i][j];
+      TRY(gemv(s.ada1, h->vec_emb, nullptr, h->vec_a, R, D, 1, 0, st)); ++n;
+      TRY(gemv(s.ada2, h->vec_a, h->vec_lora, h->mods + (size_t)(i * 3 + j) * 3 * D, 3 * D, R, 0, 0, st)); ++n;
+    }
+  TRY(gemv(h->f_ada1, h->vec_emb, nullptr, h->vec_a, R, D, 1, 0, st)); ++n;
+  TRY(gemv(h->f_ada2, h->vec_a, h->vec_lora, h->modf, 2 * D, R, 0, 0, st)); ++n;
+
+  __nv_bfloat16* k_loc = h->k_all + (size_t)h->cp_rank * L * D;
+  __nv_bfloat16* vt_loc = h->vt_all + (size_t)h->cp_rank * L * D;
+
+  for (int i = 0; i < c.num_blocks; ++i) {
+    // ---------------- FA: full self-attention (blocks.py:455-463, attention.py:247-289)
+    {
+      const SubBlock& s = h->blk[i][0];
+      const float* m = h->mods + (size_t)(i * 3 + 0) * 3 * D;
+      TRY(ln_modulate(h->x, h->pos, m, m + D, h->xn, L, D, 1e-6f, st)); ++n;   // + abs-pos add
+      TRY(gemm_bf16(h->xn, s.wk, k_loc, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st)); ++n;
+      TRY(rmsnorm_rope(k_loc, D, L, heads, s.gk, h->rope, 1e-6f, st)); ++n;
+      TRY(gemm_bf16(s.wv, h->xn, vt_loc, D, L, D, D, D, L, G3C_EPI_BF16, nullptr, 0, st)); ++n;  // V^T
+      if (h->cp_size > 1) {
+        // one in-place all-gather of K and of V^T per layer, overlapped with the Q projection
+        G3C_CUDA(cudaEventRecord(h->ev_kv, st));
+        G3C_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_kv, 0));
+        G3C_NCCL(nccl().GroupStart());
+        G3C_NCCL(nccl().AllGather(k_loc, h->k_all, (size_t)L * D, kNcclBfloat16, h->comm, h->comm_stream));
+        G3C_NCCL(nccl().AllGather(vt_loc, h->vt_all, (size_t)L * D, kNcclBfloat16, h->comm, h->comm_stream));
+        G3C_NCCL(nccl().GroupEnd());
+        G3C_CUDA(cudaEventRecord(h->ev_gathered, h->comm_stream));
+        n += 2;
+      }
+      TRY(gemm_bf16(h->xn, s.wq, h->q, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st)); ++n;
+      TRY(rmsnorm_rope(h->q, D, L, heads, s.gq, h->rope, 1e-6f, st)); ++n;
+      if (h->cp_size > 1) G3C_CUDA(cudaStreamWaitEvent(st, h->ev_gathered, 0));
+      TRY(attn_fwd(h->q, h->k_all, h->vt_all, h->att, L, Lk_all, heads, D, D, D, L, attn_scale, st)); ++n;
+      TRY(gemm_bf16(h->att, s.wo, h->x, L, D, D, D, D, D, G3C_EPI_GATED_RESIDUAL_F32, m + 2 * D, 0, st)); ++n;
+    }
+    // ---------------- CA: cross-attention to the T5 context (blocks.py:464-471)
+    {
+      const SubBlock& s = h->blk[i][1];
+      const float* m = h->mods + (size_t)(i * 3 + 1) * 3 * D;
+      const int C = c.context_dim, M = h->ctx_len;
+      TRY(ln_modulate(h->x, nullptr, m, m + D, h->xn, L, D, 1e-6f, st)); ++n;
+      TRY(gemm_bf16(ctx, s.wk, h->kc, M, D, C, C, C, D, G3C_EPI_BF16, nullptr, 0, st)); ++n;
+      TRY(rmsnorm_rope(h->kc, D, M, heads, s.gk, nullptr, 1e-6f, st)); ++n;
+      TRY(gemm_bf16(s.wv, ctx, h->vtc, D, M, C, C, C, M, G3C_EPI_BF16, nullptr, 0, st)); ++n;
+      TRY(gemm_bf16(h->xn, s.wq, h->q, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st)); ++n;
+      TRY(rmsnorm_rope(h->q, D, L, heads, s.gq, nullptr, 1e-6f, st)); ++n;
+      TRY(attn_fwd(h->q, h->kc, h->vtc, h->att, L, M, heads, D, D, D, M, attn_scale, st)); ++n;
+      TRY(gemm_bf16(h->att, s.wo, h->x, L, D, D, D, D, D, G3C_EPI_GATED_RESIDUAL_F32, m + 2 * D, 0, st)); ++n;
+    }
+    // ---------------- MLP (attention.py:91-102)
+    {
+      const SubBlock& s = h->blk[i][2];
+      const float* m = h->mods + (size_t)(i * 3 + 2) * 3 * D;
+      TRY(ln_modulate(h->x, nullptr, m, m + D, h->xn, L, D, 1e-6f, st)); ++n;
+      TRY(gemm_bf16(h->xn, s.w1, h->hid, L, F, D, D, D, F, G3C_EPI_GELU_BF16, nullptr, 0, st)); ++n;
+      TRY(gemm_bf16(h->hid, s.w2, h->x, L, D, F, F, F, D, G3C_EPI_GATED_RESIDUAL_F32, m + 2 * D, 0, st)); ++n;
+    }
+  }
+  // ---- final layer + unpatchify (blocks.py:222-242, general_dit.py:328-358)
+  const int No = c.out_channels * 4;
+  TRY(ln_modulate(h->x, nullptr, h->modf, h->modf + D, h->xn, L, D, 1e-6f, st)); ++n;
+  TRY(gemm_bf16(h->xn, h->w_final, h->yfin, L, No, D, D, D, No, G3C_EPI_F32, nullptr, 64, st)); ++n;
+  TRY(unpatchify(h->yfin, No, h->T, h->Hp, h->Wp, c.out_channels, (__nv_bfloat16*)out, st)); ++n;
+  h->launches = n;
+  return G3C_OK;
+}
+
+}  // namespace g3c
+
+extern "C" {
+
+int g3c_dit_create(const g3c_dit_config* cfg, g3c_dit_t** out) {
+  G3C_REQUIRE(cfg && out, "dit_create: null argument");
+  G3C_REQUIRE(cfg->model_channels % 128 == 0 && cfg->num_heads * 128 == cfg->model_channels,
+              "dit_create: head_dim must be 128 (model_channels=%d heads=%d)", cfg->model_channels,
+              cfg->num_heads);
+  G3C_REQUIRE(cfg->adaln_lora_dim % 8 == 0 && cfg->context_dim % 8 == 0 && cfg->ffn_dim % 8 == 0,
+              "dit_create: adaln_lora_dim/context_dim/ffn_dim must be multiples of 8");
+  G3C_REQUIRE(cfg->in_channels >= 17 && cfg->out_channels > 0 && cfg->num_blocks > 0, "dit_create: bad config");
+  g3c_dit* h = new g3c_dit();
+  h->cfg = *cfg;
+  *out = h;
+  return G3C_OK;
+}
+
+static void free_ws(g3c_dit* h) {
+  if (h->ws) cudaFree(h->ws);
+  h->ws = nullptr;
+  h->ws_bytes = 0;
+  h->L = 0;
+  h->tables_ready = false;
+}
+
+int g3c_dit_destroy(g3c_dit_t* h) {
+  if (!h) return G3C_OK;
+  free_ws(h);
+  if (h->w_patch_pad) cudaFree(h->w_patch_pad);
+  if (h->gammas) cudaFree(h->gammas);
+  if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  if (h->ev_kv) cudaEventDestroy(h->ev_kv);
+  if (h->ev_gathered) cudaEventDestroy(h->ev_gathered);
+  delete h;
+  return G3C_OK;
+}
+
+int g3c_dit_load(g3c_dit_t* h, const char* name, const void* ptr, const int64_t* shape, int ndim, int dtype) {
+  G3C_REQUIRE(h && name && ptr && shape && ndim >= 1 && ndim <= 4, "dit_load: bad arguments");
+  WTensor t;
+  t.ptr = ptr;
+  t.shape.assign(shape, shape + ndim);
+  t.dtype = dtype;
+  h->w[name] = t;
+  h->resolved = false;
+  h->tables_ready = false;
+  return G3C_OK;
+}
+
+int g3c_nccl_unique_id(void* out128) {
+  G3C_REQUIRE(out128, "nccl_unique_id: null argument");
+  if (!nccl().ok) {
+    set_error("libnccl.so.2 could not be loaded");
+    return G3C_ENCCL;
+  }
+  ncclUniqueId id;
+  G3C_NCCL(nccl().GetUniqueId(&id));
+  memcpy(out128, &id, 128);
+  return G3C_OK;
+}
+
+int g3c_dit_enable_cp(g3c_dit_t* h, const void* nccl_unique_id, int cp_rank, int cp_size) {
+  G3C_REQUIRE(h && nccl_unique_id && cp_size >= 1 && cp_rank >= 0 && cp_rank < cp_size, "enable_cp: bad arguments");
+  if (!nccl().ok) {
+    set_error("libnccl.so.2 could not be loaded");
+    return G3C_ENCCL;
+  }
+  if (h->comm) {
+    nccl().CommDestroy(h->comm);
+    h->comm = nullptr;
+  }
+  ncclUniqueId id;
+  memcpy(&id, nccl_unique_id, 128);
+  G3C_NCCL(nccl().CommInitRank(&h->comm, cp_size, id, cp_rank));
+  if (!h->comm_stream) G3C_CUDA(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+  if (!h->ev_kv) G3C_CUDA(cudaEventCreateWithFlags(&h->ev_kv, cudaEventDisableTiming));
+  if (!h->ev_gathered) G3C_CUDA(cudaEventCreateWithFlags(&h->ev_gathered, cudaEventDisableTiming));
+  h->cp_rank = cp_rank;
+  h->cp_size = cp_size;
+  free_ws(h);  // shape-dependent buffers change with cp_size
+  return G3C_OK;
+}
+
+int g3c_dit_disable_cp(g3c_dit_t* h) {
+  G3C_REQUIRE(h, "disable_cp: null handle");
+  if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
+  h->comm = nullptr;
+  h->cp_rank = 0;
+  h->cp_size = 1;
+  free_ws(h);
+  return G3C_OK;
+}
+
+int g3c_dit_set_shape(g3c_dit_t* h, int T_local, int H_latent, int W_latent, int ctx_len, float fps) {
+  G3C_REQUIRE(h, "set_shape: null handle");
+  const g3c_dit_config& c = h->cfg;
+  G3C_REQUIRE(T_local > 0 && H_latent > 0 && W_latent > 0 && H_latent % 2 == 0 && W_latent % 2 == 0,
+              "set_shape: latent H, W must be positive and even (patch 2)");
+  const int Hp = H_latent / 2, Wp = W_latent / 2;
+  G3C_REQUIRE(Hp <= c.max_h && Wp <= c.max_w && T_local * h->cp_size <= c.max_frames,
+              "set_shape: token grid %dx%dx%d exceeds the position tables", T_local * h->cp_size, Hp, Wp);
+  const long long L = (long long)T_local * Hp * Wp;
+  G3C_REQUIRE((L * h->cp_size) % 128 == 0 && L % 128 == 0,
+              "set_shape: tokens per rank (%lld) must be a multiple of 128", L);
+  G3C_REQUIRE(ctx_len > 0 && ctx_len % 128 == 0, "set_shape: ctx_len=%d must be a multiple of 128", ctx_len);
+  G3C_REQUIRE(fps > 0, "set_shape: fps must be positive");
+  if (h->ws && h->T == T_local && h->Hl == H_latent && h->Wl == W_latent && h->ctx_len == ctx_len &&
+      h->fps == fps)
+    return G3C_OK;
+  free_ws(h);
+  const size_t D = c.model_channels, F = c.ffn_dim, cp = h->cp_size;
+  const size_t Kpad = ((size_t)(c.in_channels + (c.concat_padding_mask ? 1 : 0)) * 4 + 63) / 64 * 64;
+  const size_t lat = (size_t)16 * T_local * H_latent * W_latent;
+  struct Item { void** p; size_t bytes; };
+  std::vector<Item> items = {
+      {(void**)&h->x, (size_t)L * D * 4},        {(void**)&h->xn, (size_t)L * D * 2},
+      {(void**)&h->q, (size_t)L * D * 2},        {(void**)&h->k_all, (size_t)L * D * 2 * cp},
+      {(void**)&h->vt_all, (size_t)L * D * 2 * cp}, {(void**)&h->att, (size_t)L * D * 2},
+      {(void**)&h->hid, (size_t)L * F * 2},      {(void**)&h->tok, (size_t)L * Kpad * 2},
+      {(void**)&h->pos, (size_t)L * D * 2},      {(void**)&h->kc, (size_t)ctx_len * D * 2},
+      {(void**)&h->vtc, (size_t)ctx_len * D * 2}, {(void**)&h->rope, (size_t)L * 128 * 4},
+      {(void**)&h->yfin, (size_t)L * c.out_channels * 4 * 4},
+      {(void**)&h->mods, (size_t)c.num_blocks * 3 * 3 * D * 4}, {(void**)&h->modf, 2 * D * 4},
+      {(void**)&h->vec_s, D * 4},                {(void**)&h->vec_emb, D * 4},
+      {(void**)&h->vec_h1, D * 4},               {(void**)&h->vec_lora, 3 * D * 4},
+      {(void**)&h->vec_a, (size_t)c.adaln_lora_dim * 4}, {(void**)&h->freqs, 64 * 4},
+      {(void**)&h->lat_xtilde, lat * 2},         {(void**)&h->lat_xin, lat * 2},
+      {(void**)&h->lat_oc, lat * 2},             {(void**)&h->lat_ou, lat * 2},
+  };
+  size_t total = 0;
+  for (auto& it : items) total += align_up(it.bytes, 1024);
+  cudaError_t e = cudaMalloc(&h->ws, total);
+  if (e != cudaSuccess) {
+    h->ws = nullptr;
+    set_error("dit_set_shape: cudaMalloc of %zu bytes failed: %s", total, cudaGetErrorString(e));
+    return G3C_ENOMEM;
+  }
+  size_t off = 0;
+  for (auto& it : items) {
+    *it.p = (char*)h->ws + off;
+    off += align_up(it.bytes, 1024);
+  }
+  h->ws_bytes = total;
+  h->T = T_local;
+  h->Hl = H_latent;
+  h->Wl = W_latent;
+  h->Hp = Hp;
+  h->Wp = Wp;
+  h->L = (int)L;
+  h->ctx_len = ctx_len;
+  h->fps = fps;
+  h->tables_ready = false;
+  return G3C_OK;
+}
+
+int g3c_dit_forward(g3c_dit_t* h, const void* x, const void* cond_mask, const void* cond_pose,
+                    const void* padding_mask, float timestep, const void* ctx, void* out, void* stream) {
+  return g3c::forward(h, x, cond_mask, cond_pose, padding_mask, timestep, ctx, out, (cudaStream_t)stream);
+}
+
+int g3c_denoise_step(g3c_dit_t* h, const g3c_step_args* a, void* stream) {
+  G3C_REQUIRE(h && a && a->xt && a->gt_latent && a->aug_noise && a->indicator && a->cond_mask &&
+                  a->ctx_cond && a->ctx_uncond && a->xt_next,
+              "denoise_step: null argument");
+  G3C_REQUIRE(h->L > 0, "denoise_step: g3c_dit_set_shape was not called");
+  G3C_REQUIRE(a->sigma > 0, "denoise_step: sigma must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t plane = (size_t)h->Hl * h->Wl;
+  // t = 0.25 * ln(sigma)  (EDMEulerScheduler timesteps; model_v2w.py:131-140)
+  // ... fed to the net as a bf16 tensor (model_v2w.py:140 `t.to(**self.tensor_kwargs)`)
+  const float timestep = __bfloat162float(__float2bfloat16_rn(0.25f * logf(a->sigma)));
+  TRY(sampler_pre((const __nv_bfloat16*)a->xt, (const __nv_bfloat16*)a->gt_latent, a->aug_noise,
+                  a->indicator, 16, h->T, plane, a->sigma, a->sigma_aug, a->sigma_data, h->lat_xtilde,
+                  h->lat_xin, st));
+  TRY(g3c::forward(h, h->lat_xin, a->cond_mask, a->pose_cond, a->padding_mask, timestep, a->ctx_cond,
+                   h->lat_oc, st));
+  int n1 = h->launches;
+  TRY(g3c::forward(h, h->lat_xin, a->cond_mask, nullptr, a->padding_mask, timestep, a->ctx_uncond,
+                   h->lat_ou, st));
+  TRY(sampler_post(h->lat_xtilde, h->lat_oc, h->lat_ou, (const __nv_bfloat16*)a->gt_latent, a->indicator,
+                   16, h->T, plane, a->guidance, a->sigma, a->sigma_next, a->sigma_aug, a->sigma_data,
+                   (__nv_bfloat16*)a->xt_next, st));
+  h->launches += n1 + 2;
+  return G3C_OK;
+}
+
+int64_t g3c_dit_workspace_bytes(const g3c_dit_t* h) { return h ? (int64_t)h->ws_bytes : 0; }
+int g3c_dit_last_launch_count(const g3c_dit_t* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

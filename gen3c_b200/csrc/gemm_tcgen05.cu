@@ -1,0 +1,342 @@
+// Path D — dense bf16 GEMM on the 5th-gen tensor cores:  D[M,N] = A[M,K] · B[N,K]^T  (fp32 accum)
+//
+// Every Linear of the DiT (reference: cosmos_predict1/diffusion/module/attention.py:263-266,289,
+// 91-102; blocks.py:153-163,222-242) is `y = x · W^T` with x [tokens, in] and W [out, in], i.e.
+// both operands K-major — exactly the layout tcgen05.mma consumes from 128-byte-swizzled shared
+// memory.  V^T for the attention kernel is produced by the same kernel with the operands swapped
+// (A = W_v, B = x), so no transpose pass exists anywhere.
+//
+// Structure (one persistent CTA per SM, 256 threads):
+//   warp 0      TMA producer   : cp.async.bulk.tensor A/B tiles -> smem ring (kStages), mbarrier tx
+//   warp 1      MMA issuer     : one thread, tcgen05.mma 128 x BN x 16, accumulators in TMEM,
+//                                tcgen05.commit releases smem slots / publishes accumulators
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue       : tcgen05.ld (lane = row) -> fused epilogue -> global
+// Two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "kernels.h"
+
+namespace g3c {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle span
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+
+struct GemmParams {
+  int M, N, K;
+  int ldd;             // leading dimension of D in elements
+  void* D;             // bf16 or f32
+  const float* gate;   // [N] for EPI_GATED_RESIDUAL
+  int num_m_blk, num_n_blk, num_k_blk;
+  int super_n;         // n-blocks per super-column (L2 reuse of the B operand)
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& m_blk, int& n_blk) {
+  // super-columns of `super_n` n-blocks; inside one, n fastest so that concurrently running CTAs
+  // share A row-blocks and the B super-column stays L2 resident.
+  int per_super = p.num_m_blk * p.super_n;
+  int sc = tile / per_super;
+  int rem = tile - sc * per_super;
+  int n0 = sc * p.super_n;
+  int width = p.num_n_blk - n0 < p.super_n ? p.num_n_blk - n0 : p.super_n;
+  // the last super-column may be narrower
+  if (width != p.super_n) {
+    m_blk = rem / width;
+    n_blk = n0 + rem - m_blk * width;
+  } else {
+    m_blk = rem / p.super_n;
+    n_blk = n0 + rem - m_blk * p.super_n;
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+    k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+           const GemmParams p) {
+  using S = GemmSmem<BN>;
+  constexpr int kStages = S::kStages;
+  constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                 : (2 * BN <= 256) ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * S::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint64_t* full = bars;                    // [kStages]
+  uint64_t* empty = bars + kStages;         // [kStages]
+  uint64_t* tfull = bars + 2 * kStages;     // [2]
+  uint64_t* tempty = bars + 2 * kStages + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_tiles = p.num_m_blk * p.num_n_blk;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(p, tile, m_blk, n_blk);
+        for (int kb = 0; kb < p.num_k_blk; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], S::kStageBytes);
+          tma_load_2d(smem_a + stage * S::kABytes, &tmA, &full[stage], kb * BK, m_blk * BM);
+          tma_load_2d(smem_b + stage * S::kBBytes, &tmB, &full[stage], kb * BK, n_blk * BN);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer (single thread) =====
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_k_blk; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_sdesc_sw128(smem_u32(smem_a + stage * S::kABytes));
+          const uint64_t db = make_sdesc_sw128(smem_u32(smem_b + stage * S::kBBytes));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            umma_ss(d_tmem, sdesc_advance(da, k * UMMA_K * 2), sdesc_advance(db, k * UMMA_K * 2),
+                    idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[as]);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const uint32_t ew = warp - 4;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    uint32_t as = 0, aphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      tile_coords(p, tile, m_blk, n_blk);
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const int row = m_blk * BM + ew * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((ew * 32u) << 16) + as * BN + c * 32, r);
+        tc_wait_ld();
+        const int col0 = n_blk * BN + c * 32;
+        if (row_ok && col0 < p.N) {
+          const bool full_chunk = col0 + 32 <= p.N;
+          if constexpr (EPI == G3C_EPI_BF16 || EPI == G3C_EPI_GELU_BF16) {
+            __nv_bfloat16* dptr = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col0;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              v[i] = __uint_as_float(r[i]);
+              if constexpr (EPI == G3C_EPI_GELU_BF16) v[i] = gelu_erf(v[i]);
+            }
+            if (full_chunk) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 q;
+                q.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+                q.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+                q.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+                q.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+                reinterpret_cast<uint4*>(dptr)[i] = q;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) dptr[i] = __float2bfloat16_rn(v[i]);
+            }
+          } else {
+            float* dptr = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
+            if (full_chunk) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 acc = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                         __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+                if constexpr (EPI == G3C_EPI_GATED_RESIDUAL_F32) {
+                  float4 g = *reinterpret_cast<const float4*>(p.gate + col0 + 4 * i);
+                  float4 x = reinterpret_cast<float4*>(dptr)[i];
+                  acc.x = fmaf(g.x, acc.x, x.x);
+                  acc.y = fmaf(g.y, acc.y, x.y);
+                  acc.z = fmaf(g.z, acc.z, x.z);
+                  acc.w = fmaf(g.w, acc.w, x.w);
+                }
+                reinterpret_cast<float4*>(dptr)[i] = acc;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (col0 + i < p.N) {
+                  float a = __uint_as_float(r[i]);
+                  if constexpr (EPI == G3C_EPI_GATED_RESIDUAL_F32) a = fmaf(p.gate[col0 + i], a, dptr[i]);
+                  dptr[i] = a;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int BN, int EPI>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                       cudaStream_t st) {
+  using S = GemmSmem<BN>;
+  static bool configured = false;
+  if (!configured) {
+    G3C_CUDA(cudaFuncSetAttribute(k_gemm<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  S::kTotal));
+    configured = true;
+  }
+  int tiles = p.num_m_blk * p.num_n_blk;
+  int grid = tiles < sm_count() ? tiles : sm_count();
+  k_gemm<BN, EPI><<<grid, GEMM_THREADS, S::kTotal, st>>>(tmA, tmB, p);
+  G3C_CUDA(cudaGetLastError());
+  return G3C_OK;
+}
+
+template <int BN>
+static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                        cudaStream_t st) {
+  switch (epi) {
+    case G3C_EPI_BF16: return launch_gemm<BN, G3C_EPI_BF16>(tmA, tmB, p, st);
+    case G3C_EPI_GELU_BF16: return launch_gemm<BN, G3C_EPI_GELU_BF16>(tmA, tmB, p, st);
+    case G3C_EPI_GATED_RESIDUAL_F32: return launch_gemm<BN, G3C_EPI_GATED_RESIDUAL_F32>(tmA, tmB, p, st);
+    case G3C_EPI_F32: return launch_gemm<BN, G3C_EPI_F32>(tmA, tmB, p, st);
+  }
+  set_error("gemm: unknown epilogue %d", epi);
+  return G3C_EINVAL;
+}
+
+// Host entry used by the engine and by the C ABI.
+int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
+              int epilogue, const float* gate, int block_n, cudaStream_t st) {
+  G3C_REQUIRE(A && B && D, "gemm: null operand");
+  G3C_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape %dx%dx%d", M, N, K);
+  G3C_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "gemm: K/lda/ldb must be multiples of 8");
+  G3C_REQUIRE(lda >= K && ldb >= K && ldd >= N, "gemm: leading dimension smaller than extent");
+  if (epilogue == G3C_EPI_BF16 || epilogue == G3C_EPI_GELU_BF16)
+    G3C_REQUIRE(ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0,
+                "gemm: bf16 output needs ldd %% 8 == 0 and 16-byte aligned base");
+  else
+    G3C_REQUIRE(ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0,
+                "gemm: f32 output needs ldd %% 4 == 0 and 16-byte aligned base");
+  G3C_REQUIRE(epilogue != G3C_EPI_GATED_RESIDUAL_F32 ||
+                  (gate && (reinterpret_cast<uintptr_t>(gate) & 15) == 0),
+              "gemm: gated-residual epilogue needs a 16-byte aligned gate vector");
+  int bn = block_n;
+  if (bn == 0) bn = (N >= 256 && N % 256 == 0) ? 256 : (N > 64 ? 128 : 64);
+  G3C_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: block_n %d unsupported", bn);
+
+  CUtensorMap tmA, tmB;
+  uint64_t dimsA[2] = {(uint64_t)K, (uint64_t)M}, strA[1] = {(uint64_t)lda * 2};
+  uint32_t boxA[2] = {BK, BM};
+  int rc = make_tmap_bf16_sw128(&tmA, A, 2, dimsA, strA, boxA);
+  if (rc) return rc;
+  uint64_t dimsB[2] = {(uint64_t)K, (uint64_t)N}, strB[1] = {(uint64_t)ldb * 2};
+  uint32_t boxB[2] = {BK, (uint32_t)bn};
+  rc = make_tmap_bf16_sw128(&tmB, B, 2, dimsB, strB, boxB);
+  if (rc) return rc;
+
+  GemmParams p;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.ldd = ldd;
+  p.D = D;
+  p.gate = gate;
+  p.num_m_blk = (M + BM - 1) / BM;
+  p.num_n_blk = (N + bn - 1) / bn;
+  p.num_k_blk = (K + BK - 1) / BK;
+  // keep one super-column of B (super_n * bn * K * 2 bytes) well inside the 126 MB L2
+  long long col_bytes = (long long)bn * K * 2;
+  int sn = (int)((48ll << 20) / (col_bytes > 0 ? col_bytes : 1));
+  if (sn < 1) sn = 1;
+  if (sn > p.num_n_blk) sn = p.num_n_blk;
+  p.super_n = sn;
+  switch (bn) {
+    case 64: return dispatch_epi<64>(epilogue, tmA, tmB, p, st);
+    case 128: return dispatch_epi<128>(epilogue, tmA, tmB, p, st);
+    default: return dispatch_epi<256>(epilogue, tmA, tmB, p, st);
+  }
+}
+
+}  // namespace g3c
+
+extern "C" int g3c_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda,
+                             int ldb, int ldd, int epilogue, const float* gate, int block_n,
+                             void* stream) {
+  return g3c::gemm_bf16(A, B, D, M, N, K, lda, ldb, ldd, epilogue, gate, block_n,
+                        (cudaStream_t)stream);
+}

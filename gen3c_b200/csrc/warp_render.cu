@@ -1,0 +1,545 @@
+// Path R — 3D-cache render: project cached world points into the target camera, depth-weighted
+// bilinear (4-corner) splat with fp32 vector atomics into a padded accumulation buffer, normalise.
+//
+// Re-designed from the arithmetic of the reference (cited per function), not from its op graph:
+//   reference: cosmos_predict1/diffusion/inference/forward_warp_utils_pytorch.py
+//     project_points      :462-486     forward_warp (depth1=None branch) :219-250,281-284
+//     bilinear_splatting  :576-695     create_grid :697-703     unproject_points :410-460
+//     reliable_depth_mask_range_batch :338-353
+//   reference: cosmos_predict1/diffusion/inference/cache_3d.py  render_cache :151-236
+//
+// Three passes over a batch of items that stays L2-resident:
+//   pass 1  k_project_max : z = (K·(w2c·[p;1])).z ; per-group max of log1p(max(z,0))  (warp
+//                           shuffle + block reduce + one atomicMax per block)
+//   pass 2  k_splat       : recompute the projection (cheaper than a round trip through HBM),
+//                           4 x red.global.add.v4.f32 {r*w, g*w, b*w, w} per source pixel
+//   pass 3  k_normalise   : crop the 1-px ring, acc/w, fill, clamp, write planar outputs
+// HBM-bound by design: algorithmic traffic 44 B/px.
+#include "common.cuh"
+
+namespace g3c {
+
+struct Cam {
+  float w[12];  // first three rows of w2c
+  float k[9];
+};
+
+__device__ __forceinline__ Cam load_cam(const float* __restrict__ w2c, const float* __restrict__ K) {
+  Cam c;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) c.w[i] = __ldg(w2c + i);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) c.k[i] = __ldg(K + i);
+  return c;
+}
+
+// q = K · (w2c · [p;1])[:3]   — explicit rounding order so that pass 1 and pass 2 agree bit for bit
+// (reference: project_points :469-479)
+__device__ __forceinline__ void project(const Cam& c, float px, float py, float pz, float& qx,
+                                        float& qy, float& qz) {
+  float cx = __fadd_rn(__fmaf_rn(c.w[2], pz, __fmaf_rn(c.w[1], py, __fmul_rn(c.w[0], px))), c.w[3]);
+  float cy = __fadd_rn(__fmaf_rn(c.w[6], pz, __fmaf_rn(c.w[5], py, __fmul_rn(c.w[4], px))), c.w[7]);
+  float cz = __fadd_rn(__fmaf_rn(c.w[10], pz, __fmaf_rn(c.w[9], py, __fmul_rn(c.w[8], px))), c.w[11]);
+  qx = __fmaf_rn(c.k[2], cz, __fmaf_rn(c.k[1], cy, __fmul_rn(c.k[0], cx)));
+  qy = __fmaf_rn(c.k[5], cz, __fmaf_rn(c.k[4], cy, __fmul_rn(c.k[3], cx)));
+  qz = __fmaf_rn(c.k[8], cz, __fmaf_rn(c.k[7], cy, __fmul_rn(c.k[6], cx)));
+}
+
+// Destination indices and clamped position of one source pixel.
+// reference: bilinear_splatting :605-621 — floor/ceil are taken BEFORE clamping the position;
+// all three are clamped to x in [0, W+1], y in [0, H+1].
+struct SplatIdx {
+  int fx, fy, cx, cy;
+  float px, py;  // clamped positions
+};
+__device__ __forceinline__ SplatIdx splat_indices(float flow_x, float flow_y, int x, int y, int W,
+                                                  int H) {
+  SplatIdx s;
+  float pos_x = __fadd_rn(__fadd_rn(flow_x, (float)x), 1.0f);
+  float pos_y = __fadd_rn(__fadd_rn(flow_y, (float)y), 1.0f);
+  float wmax = (float)(W + 1), hmax = (float)(H + 1);
+  // fmaxf(NaN, 0) = 0: NaN coordinates land on the cropped border, as torch's GPU float->long does
+  s.fx = (int)fminf(fmaxf(floorf(pos_x), 0.0f), wmax);
+  s.cx = (int)fminf(fmaxf(ceilf(pos_x), 0.0f), wmax);
+  s.fy = (int)fminf(fmaxf(floorf(pos_y), 0.0f), hmax);
+  s.cy = (int)fminf(fmaxf(ceilf(pos_y), 0.0f), hmax);
+  s.px = fminf(fmaxf(pos_x, 0.0f), wmax);
+  s.py = fminf(fmaxf(pos_y, 0.0f), hmax);
+  return s;
+}
+
+__device__ __forceinline__ float log_depth(float z) { return log1pf(fmaxf(z, 0.0f)); }
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b),
+               "f"(c), "f"(d)
+               : "memory");
+}
+
+// lz >= 0 or NaN, so the int ordering of the bit pattern equals the float ordering.
+__device__ __forceinline__ void block_atomic_max(float v, float* dst) {
+  __shared__ float red[32];
+  v = warp_max(v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+    float m = lane < nw ? red[lane] : 0.0f;
+    m = warp_max(m);
+    if (lane == 0) atomicMax(reinterpret_cast<int*>(dst), __float_as_int(m));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 1: per-group max of log1p(max(z,0))
+// item i: camera index cam_of(i) = i / N ; source index = src_bcast ? (i/(N*F))*N + i%N : i
+// ------------------------------------------------------------------------------------------------
+struct ItemMap {
+  int N;          // buffers per camera
+  int F;          // cameras (target frames) per batch element
+  int src_bcast;  // 1: cache has a single frame broadcast over F targets
+  __device__ __forceinline__ int cam(int i) const { return i / N; }
+  __device__ __forceinline__ int src(int i) const {
+    return src_bcast ? (i / (N * F)) * N + (i % N) : i;
+  }
+};
+
+__global__ void __launch_bounds__(256) k_project_max(const float* __restrict__ points,
+                                                    const float* __restrict__ w2c,
+                                                    const float* __restrict__ K, ItemMap map,
+                                                    int item0, int HW, int group, float* gmax) {
+  int item = item0 + blockIdx.y;
+  Cam c = load_cam(w2c + 16 * map.cam(item), K + 9 * map.cam(item));
+  const float* p = points + (size_t)map.src(item) * HW * 3;
+  float m = 0.0f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    float qx, qy, qz;
+    project(c, p[3 * i], p[3 * i + 1], p[3 * i + 2], qx, qy, qz);
+    float lz = log_depth(qz);
+    m = (lz > m || lz != lz) ? lz : m;  // propagate NaN like torch.max
+  }
+  block_atomic_max(m, gmax + item / group);
+}
+
+__global__ void __launch_bounds__(256) k_depth_max(const float* __restrict__ depth, size_t n,
+                                                  float* gmax) {
+  float m = 0.0f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    float lz = log_depth(depth[i]);
+    m = (lz > m || lz != lz) ? lz : m;
+  }
+  block_atomic_max(m, gmax);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 2: splat.  acc: [items_in_pass][H+2][W+2][4] = {c0*w, c1*w, c2*w, w};  accz: [..][H+2][W+2]
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void splat_pixel(float* __restrict__ acc, float* __restrict__ accz,
+                                            const SplatIdx& s, float z, float lz_max, float mask,
+                                            float v0, float v1, float v2, int W) {
+  // reference :623-634
+  float dyf = __fsub_rn(1.0f, __fsub_rn(s.py, (float)s.fy));
+  float dyc = __fsub_rn(1.0f, __fsub_rn((float)s.cy, s.py));
+  float dxf = __fsub_rn(1.0f, __fsub_rn(s.px, (float)s.fx));
+  float dxc = __fsub_rn(1.0f, __fsub_rn((float)s.cx, s.px));
+  // reference :638-646
+  float lz = log_depth(z);
+  float e = __fmul_rn(__fdiv_rn(lz, __fadd_rn(lz_max, 1e-7f)), 50.0f);
+  e = fminf(e, 80.0f);
+  float dw = __fadd_rn(expf(e), 1e-7f);
+  float w_nw = __fdiv_rn(__fmul_rn(__fmul_rn(dyf, dxf), mask), dw);
+  float w_sw = __fdiv_rn(__fmul_rn(__fmul_rn(dyc, dxf), mask), dw);
+  float w_ne = __fdiv_rn(__fmul_rn(__fmul_rn(dyf, dxc), mask), dw);
+  float w_se = __fdiv_rn(__fmul_rn(__fmul_rn(dyc, dxc), mask), dw);
+  const int Wp = W + 2;
+  size_t i_nw = (size_t)s.fy * Wp + s.fx, i_sw = (size_t)s.cy * Wp + s.fx;
+  size_t i_ne = (size_t)s.fy * Wp + s.cx, i_se = (size_t)s.cy * Wp + s.cx;
+  // a zero weight adds +0 to every slot: skip the atomics (identical result for finite inputs)
+  if (w_nw != 0.0f) red_add_v4(acc + 4 * i_nw, v0 * w_nw, v1 * w_nw, v2 * w_nw, w_nw);
+  if (w_sw != 0.0f) red_add_v4(acc + 4 * i_sw, v0 * w_sw, v1 * w_sw, v2 * w_sw, w_sw);
+  if (w_ne != 0.0f) red_add_v4(acc + 4 * i_ne, v0 * w_ne, v1 * w_ne, v2 * w_ne, w_ne);
+  if (w_se != 0.0f) red_add_v4(acc + 4 * i_se, v0 * w_se, v1 * w_se, v2 * w_se, w_se);
+  if (accz) {
+    if (w_nw != 0.0f) atomicAdd(accz + i_nw, z * w_nw);
+    if (w_sw != 0.0f) atomicAdd(accz + i_sw, z * w_sw);
+    if (w_ne != 0.0f) atomicAdd(accz + i_ne, z * w_ne);
+    if (w_se != 0.0f) atomicAdd(accz + i_se, z * w_se);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_splat_points(const float* __restrict__ points, const float* __restrict__ image,
+                   const float* __restrict__ mask, const float* __restrict__ w2c,
+                   const float* __restrict__ K, ItemMap map, int item0, int C, int H, int W,
+                   int group, const float* __restrict__ gmax, float* __restrict__ acc,
+                   float* __restrict__ accz, float* __restrict__ flow_out) {
+  const int HW = H * W;
+  int item = item0 + blockIdx.y;
+  int src = map.src(item);
+  Cam c = load_cam(w2c + 16 * map.cam(item), K + 9 * map.cam(item));
+  const float* p = points + (size_t)src * HW * 3;
+  const float* img = image + (size_t)src * C * HW;
+  const float* msk = mask ? mask + (size_t)src * HW : nullptr;
+  float lz_max = gmax[item / group];
+  float* a = acc + (size_t)blockIdx.y * (H + 2) * (W + 2) * 4;
+  float* az = accz ? accz + (size_t)blockIdx.y * (H + 2) * (W + 2) : nullptr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    int y = i / W, x = i - y * W;
+    float qx, qy, qz;
+    project(c, p[3 * i], p[3 * i + 1], p[3 * i + 2], qx, qy, qz);
+    // reference forward_warp :244-250
+    float m = (msk ? msk[i] : 1.0f) * (qz > 0.0f ? 1.0f : 0.0f);
+    float den = __fadd_rn(qz, 1e-7f);
+    float fx = __fsub_rn(__fdiv_rn(qx, den), (float)x);
+    float fy = __fsub_rn(__fdiv_rn(qy, den), (float)y);
+    if (flow_out) {
+      flow_out[((size_t)item * 2) * HW + i] = fx;
+      flow_out[((size_t)item * 2 + 1) * HW + i] = fy;
+    }
+    SplatIdx s = splat_indices(fx, fy, x, y, W, H);
+    float v0 = img[i], v1 = C > 1 ? img[HW + i] : 0.0f, v2 = C > 2 ? img[2 * HW + i] : 0.0f;
+    splat_pixel(a, az, s, qz, lz_max, m, v0, v1, v2, W);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_splat_flow(const float* __restrict__ frame, const float* __restrict__ mask,
+                 const float* __restrict__ depth, const float* __restrict__ flow, int item0, int C,
+                 int H, int W, const float* __restrict__ gmax, float* __restrict__ acc) {
+  const int HW = H * W;
+  int item = item0 + blockIdx.y;
+  const float* img = frame + (size_t)item * C * HW;
+  float lz_max = gmax[0];
+  float* a = acc + (size_t)blockIdx.y * (H + 2) * (W + 2) * 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    int y = i / W, x = i - y * W;
+    float fx = flow[((size_t)item * 2) * HW + i], fy = flow[((size_t)item * 2 + 1) * HW + i];
+    float m = mask ? mask[(size_t)item * HW + i] : 1.0f;
+    SplatIdx s = splat_indices(fx, fy, x, y, W, H);
+    float v0 = img[i], v1 = C > 1 ? img[HW + i] : 0.0f, v2 = C > 2 ? img[2 * HW + i] : 0.0f;
+    splat_pixel(a, nullptr, s, depth[(size_t)item * HW + i], lz_max, m, v0, v1, v2, W);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_splat_indices(const float* __restrict__ flow, int H, int W, int32_t* __restrict__ idx) {
+  const int HW = H * W;
+  int item = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    int y = i / W, x = i - y * W;
+    SplatIdx s = splat_indices(flow[((size_t)item * 2) * HW + i],
+                               flow[((size_t)item * 2 + 1) * HW + i], x, y, W, H);
+    int32_t* o = idx + (size_t)item * 4 * HW;
+    o[i] = s.fx;
+    o[HW + i] = s.fy;
+    o[2 * HW + i] = s.cx;
+    o[3 * HW + i] = s.cy;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 3: crop + normalise (reference :680-695)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_normalise(const float* __restrict__ acc, const float* __restrict__ accz, int item0, int C,
+                int H, int W, int is_image, float* __restrict__ out, float* __restrict__ mask_out,
+                float* __restrict__ depth_out) {
+  const int HW = H * W;
+  int item = item0 + blockIdx.y;
+  const float4* a = reinterpret_cast<const float4*>(acc) + (size_t)blockIdx.y * (H + 2) * (W + 2);
+  const float* az = accz ? accz + (size_t)blockIdx.y * (H + 2) * (W + 2) : nullptr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    int y = i / W, x = i - y * W;
+    size_t j = (size_t)(y + 1) * (W + 2) + (x + 1);
+    float4 v = a[j];
+    float w = v.w;
+    if (w != w) w = 1000.0f;                  // nan_to_num(nan=1000)
+    else if (isinf(w)) w = w > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+    bool hit = w > 0.0f;
+    float zero = is_image ? -1.0f : 0.0f;
+    float o0 = hit ? __fdiv_rn(v.x, w) : zero;
+    float o1 = hit ? __fdiv_rn(v.y, w) : zero;
+    float o2 = hit ? __fdiv_rn(v.z, w) : zero;
+    if (is_image) {
+      o0 = fminf(fmaxf(o0, -1.0f), 1.0f);
+      o1 = fminf(fmaxf(o1, -1.0f), 1.0f);
+      o2 = fminf(fmaxf(o2, -1.0f), 1.0f);
+    }
+    float* o = out + (size_t)item * C * HW;
+    o[i] = o0;
+    if (C > 1) o[HW + i] = o1;
+    if (C > 2) o[2 * HW + i] = o2;
+    if (mask_out) mask_out[(size_t)item * HW + i] = hit ? 1.0f : 0.0f;
+    if (depth_out) depth_out[(size_t)item * HW + i] = hit ? __fdiv_rn(az[j], w) : 0.0f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// unproject (reference :410-460) and the 5x5 reliability mask (:338-353)
+// ------------------------------------------------------------------------------------------------
+// Inverses in double (Gauss-Jordan with partial pivoting), rounded to fp32 — reference uses
+// torch.linalg.inv in fp32 (:147-148); agreement is at fp32 round-off, stated in the tests.
+__device__ void invert_small(const float* __restrict__ m, int n, float* __restrict__ out) {
+  double a[4][8];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) {
+      a[i][j] = m[i * n + j];
+      a[i][n + j] = (i == j) ? 1.0 : 0.0;
+    }
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    for (int r = c + 1; r < n; ++r)
+      if (fabs(a[r][c]) > fabs(a[piv][c])) piv = r;
+    if (piv != c)
+      for (int j = 0; j < 2 * n; ++j) {
+        double t = a[c][j];
+        a[c][j] = a[piv][j];
+        a[piv][j] = t;
+      }
+    double d = 1.0 / a[c][c];
+    for (int j = 0; j < 2 * n; ++j) a[c][j] *= d;
+    for (int r = 0; r < n; ++r)
+      if (r != c) {
+        double f = a[r][c];
+        for (int j = 0; j < 2 * n; ++j) a[r][j] -= f * a[c][j];
+      }
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) out[i * n + j] = (float)a[i][n + j];
+}
+
+__global__ void __launch_bounds__(256)
+    k_unproject(const float* __restrict__ depth, const float* __restrict__ w2c,
+                const float* __restrict__ K, const uint8_t* __restrict__ mask, int H, int W,
+                int is_depth, float* __restrict__ points) {
+  __shared__ float kinv[9];
+  __shared__ float c2w[16];
+  int item = blockIdx.y;
+  if (threadIdx.x == 0) invert_small(K + 9 * item, 3, kinv);
+  if (threadIdx.x == 32) invert_small(w2c + 16 * item, 4, c2w);
+  __syncthreads();
+  const int HW = H * W;
+  const float* d = depth + (size_t)item * HW;
+  float* out = points + (size_t)item * HW * 3;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    int y = i / W, x = i - y * W;
+    float z = d[i];
+    bool valid = mask ? mask[(size_t)item * HW + i] != 0 : z > 0.0f;
+    float ox = 0.f, oy = 0.f, oz = 0.f;
+    if (valid) {
+      float fx = (float)x, fy = (float)y;
+      float rx = __fadd_rn(__fmaf_rn(kinv[1], fy, __fmul_rn(kinv[0], fx)), kinv[2]);
+      float ry = __fadd_rn(__fmaf_rn(kinv[4], fy, __fmul_rn(kinv[3], fx)), kinv[5]);
+      float rz = __fadd_rn(__fmaf_rn(kinv[7], fy, __fmul_rn(kinv[6], fx)), kinv[8]);
+      if (!is_depth) {
+        float nrm = __fadd_rn(sqrtf(rx * rx + ry * ry + rz * rz), 1e-8f);
+        rx = __fdiv_rn(rx, nrm);
+        ry = __fdiv_rn(ry, nrm);
+        rz = __fdiv_rn(rz, nrm);
+      }
+      float cx = z * rx, cy = z * ry, cz = z * rz;
+      ox = __fadd_rn(__fmaf_rn(c2w[2], cz, __fmaf_rn(c2w[1], cy, __fmul_rn(c2w[0], cx))), c2w[3]);
+      oy = __fadd_rn(__fmaf_rn(c2w[6], cz, __fmaf_rn(c2w[5], cy, __fmul_rn(c2w[4], cx))), c2w[7]);
+      oz = __fadd_rn(__fmaf_rn(c2w[10], cz, __fmaf_rn(c2w[9], cy, __fmul_rn(c2w[8], cx))), c2w[11]);
+    }
+    out[3 * i] = ox;
+    out[3 * i + 1] = oy;
+    out[3 * i + 2] = oz;
+  }
+}
+
+// max/min pool pad with -inf/+inf (ignored), avg pool pads with zeros and divides by window^2
+// (torch defaults: count_include_pad=True).
+__global__ void __launch_bounds__(256)
+    k_reliable_mask(const float* __restrict__ depth, int H, int W, int win, float thresh, float eps,
+                    uint8_t* __restrict__ out) {
+  const int HW = H * W;
+  int item = blockIdx.y;
+  const float* d = depth + (size_t)item * HW;
+  int r = win / 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    int y = i / W, x = i - y * W;
+    float mx = -INFINITY, mn = INFINITY, sum = 0.0f;
+    for (int dy = -r; dy <= r; ++dy) {
+      int yy = y + dy;
+      if (yy < 0 || yy >= H) continue;
+      for (int dx = -r; dx <= r; ++dx) {
+        int xx = x + dx;
+        if (xx < 0 || xx >= W) continue;
+        float v = d[yy * W + xx];
+        mx = fmaxf(mx, v);
+        mn = fminf(mn, v);
+        sum += v;
+      }
+    }
+    float mean = sum / (float)(win * win);
+    float ratio = __fdiv_rn(mx - mn, mean + eps);
+    out[(size_t)item * HW + i] = (ratio < thresh && d[i] > 0.0f) ? 1 : 0;
+  }
+}
+
+}  // namespace g3c
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace g3c;
+
+struct g3c_render {
+  int H, W, max_items;
+  float* acc;   // [max_items][H+2][W+2][4]
+  float* accz;  // [max_items][H+2][W+2]
+  float* gmax;  // per-group maxima
+  int gmax_cap;
+};
+
+static inline dim3 px_grid(int HW, int items) {
+  int bx = (HW + 255) / 256;
+  int cap = 4 * sm_count();
+  if (bx > cap) bx = cap;
+  return dim3(bx, items);
+}
+
+extern "C" {
+
+int g3c_render_create(int H, int W, int max_items_per_pass, g3c_render_t** out) {
+  G3C_REQUIRE(H > 0 && W > 0 && max_items_per_pass > 0 && out, "render_create: bad arguments");
+  g3c_render* r = new g3c_render();
+  r->H = H;
+  r->W = W;
+  r->max_items = max_items_per_pass;
+  r->gmax_cap = 4096;
+  size_t plane = (size_t)(H + 2) * (W + 2);
+  cudaError_t e = cudaMalloc(&r->acc, plane * 4 * sizeof(float) * max_items_per_pass);
+  if (e == cudaSuccess) e = cudaMalloc(&r->accz, plane * sizeof(float) * max_items_per_pass);
+  if (e == cudaSuccess) e = cudaMalloc(&r->gmax, sizeof(float) * r->gmax_cap);
+  if (e != cudaSuccess) {
+    delete r;
+    return cuda_fail(e, "cudaMalloc(render workspace)", __FILE__, __LINE__);
+  }
+  *out = r;
+  return G3C_OK;
+}
+
+int g3c_render_destroy(g3c_render_t* r) {
+  if (!r) return G3C_OK;
+  cudaFree(r->acc);
+  cudaFree(r->accz);
+  cudaFree(r->gmax);
+  delete r;
+  return G3C_OK;
+}
+
+// Shared driver: items = n_cam * N flattened with N fastest; groups of `group` consecutive items
+// share one max (reference chunking: cache_3d.py:175,183 -> group = 2; forward_warp -> group = b).
+static int render_items(g3c_render* r, const float* points, const float* image, const float* mask,
+                        const float* w2c, const float* K, ItemMap map, int n_items, int C,
+                        int group, int is_image, int want_depth, float* out, float* mask_out,
+                        float* depth_out, float* flow_out, cudaStream_t st) {
+  const int H = r->H, W = r->W, HW = H * W;
+  int n_groups = (n_items + group - 1) / group;
+  G3C_REQUIRE(n_groups <= r->gmax_cap, "render: %d groups exceed workspace (%d)", n_groups,
+              r->gmax_cap);
+  G3C_REQUIRE(C >= 1 && C <= 3, "render: C=%d unsupported (1..3)", C);
+  G3C_CUDA(cudaMemsetAsync(r->gmax, 0, sizeof(float) * n_groups, st));
+  for (int i0 = 0; i0 < n_items; i0 += 65535) {
+    int n = n_items - i0 < 65535 ? n_items - i0 : 65535;
+    k_project_max<<<px_grid(HW, n), 256, 0, st>>>(points, w2c, K, map, i0, HW, group, r->gmax);
+  }
+  size_t plane = (size_t)(H + 2) * (W + 2);
+  for (int i0 = 0; i0 < n_items; i0 += r->max_items) {
+    int n = n_items - i0 < r->max_items ? n_items - i0 : r->max_items;
+    G3C_CUDA(cudaMemsetAsync(r->acc, 0, plane * 4 * sizeof(float) * n, st));
+    if (want_depth) G3C_CUDA(cudaMemsetAsync(r->accz, 0, plane * sizeof(float) * n, st));
+    k_splat_points<<<px_grid(HW, n), 256, 0, st>>>(points, image, mask, w2c, K, map, i0, C, H, W,
+                                                   group, r->gmax, r->acc,
+                                                   want_depth ? r->accz : nullptr, flow_out);
+    k_normalise<<<px_grid(HW, n), 256, 0, st>>>(r->acc, want_depth ? r->accz : nullptr, i0, C, H,
+                                                W, is_image, out, mask_out,
+                                                want_depth ? depth_out : nullptr);
+  }
+  G3C_CUDA(cudaGetLastError());
+  return G3C_OK;
+}
+
+int g3c_forward_warp(g3c_render_t* r, const float* points, const float* image, const float* mask,
+                     const float* w2c, const float* K, int b, int C, int flags, float* warped,
+                     float* mask_out, float* depth_out, float* flow_out, void* stream) {
+  G3C_REQUIRE(r && points && image && w2c && K && warped && mask_out && b > 0,
+              "forward_warp: null argument");
+  int want_depth = (flags & G3C_WARP_RENDER_DEPTH) != 0;
+  G3C_REQUIRE(!want_depth || depth_out, "forward_warp: render_depth set but depth_out is NULL");
+  ItemMap map{1, b, 0};
+  return render_items(r, points, image, mask, w2c, K, map, b, C, /*group=*/b,
+                      (flags & G3C_WARP_NOT_IMAGE) ? 0 : 1, want_depth, warped, mask_out, depth_out,
+                      flow_out, (cudaStream_t)stream);
+}
+
+int g3c_render_cache(g3c_render_t* r, const float* points, const float* images, const float* masks,
+                     const float* w2cs, const float* Ks, int B, int F_target, int N, int src_frames,
+                     int render_depth, float* pixels, float* masks_out, float* depth_out,
+                     void* stream) {
+  G3C_REQUIRE(r && points && images && w2cs && Ks && pixels && masks_out, "render_cache: null argument");
+  G3C_REQUIRE(B > 0 && F_target > 0 && N > 0, "render_cache: bad sizes");
+  G3C_REQUIRE(src_frames == 1 || src_frames == F_target,
+              "render_cache: cache has %d frames, targets %d (must be 1 or equal)", src_frames,
+              F_target);
+  G3C_REQUIRE(!render_depth || depth_out, "render_cache: render_depth set but depth_out is NULL");
+  ItemMap map{N, F_target, src_frames == 1 ? 1 : 0};
+  return render_items(r, points, images, masks, w2cs, Ks, map, B * F_target * N, 3,
+                      /*group=*/2, 1, render_depth, pixels, masks_out, depth_out, nullptr,
+                      (cudaStream_t)stream);
+}
+
+int g3c_bilinear_splatting(g3c_render_t* r, const float* frame, const float* mask,
+                           const float* depth, const float* flow, int b, int C, int is_image,
+                           float* out, float* mask_out, void* stream) {
+  G3C_REQUIRE(r && frame && depth && flow && out && mask_out && b > 0,
+              "bilinear_splatting: null argument");
+  G3C_REQUIRE(C >= 1 && C <= 3, "bilinear_splatting: C=%d unsupported (1..3)", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = r->H, W = r->W, HW = H * W;
+  G3C_CUDA(cudaMemsetAsync(r->gmax, 0, sizeof(float), st));
+  k_depth_max<<<4 * sm_count(), 256, 0, st>>>(depth, (size_t)b * HW, r->gmax);
+  size_t plane = (size_t)(H + 2) * (W + 2);
+  for (int i0 = 0; i0 < b; i0 += r->max_items) {
+    int n = b - i0 < r->max_items ? b - i0 : r->max_items;
+    G3C_CUDA(cudaMemsetAsync(r->acc, 0, plane * 4 * sizeof(float) * n, st));
+    k_splat_flow<<<px_grid(HW, n), 256, 0, st>>>(frame, mask, depth, flow, i0, C, H, W, r->gmax,
+                                                 r->acc);
+    k_normalise<<<px_grid(HW, n), 256, 0, st>>>(r->acc, nullptr, i0, C, H, W, is_image, out,
+                                                mask_out, nullptr);
+  }
+  G3C_CUDA(cudaGetLastError());
+  return G3C_OK;
+}
+
+int g3c_splat_indices(const float* flow, int b, int H, int W, int32_t* idx, void* stream) {
+  G3C_REQUIRE(flow && idx && b > 0 && H > 0 && W > 0, "splat_indices: bad arguments");
+  k_splat_indices<<<px_grid(H * W, b), 256, 0, (cudaStream_t)stream>>>(flow, H, W, idx);
+  G3C_CUDA(cudaGetLastError());
+  return G3C_OK;
+}
+
+int g3c_unproject_points(const float* depth, const float* w2c, const float* K, const uint8_t* mask,
+                         int b, int H, int W, int is_depth, float* points, void* stream) {
+  G3C_REQUIRE(depth && w2c && K && points && b > 0 && H > 0 && W > 0, "unproject: bad arguments");
+  k_unproject<<<px_grid(H * W, b), 256, 0, (cudaStream_t)stream>>>(depth, w2c, K, mask, H, W,
+                                                                   is_depth, points);
+  G3C_CUDA(cudaGetLastError());
+  return G3C_OK;
+}
+
+int g3c_reliable_depth_mask(const float* depth, int b, int H, int W, int window, float ratio_thresh,
+                            float eps, uint8_t* out, void* stream) {
+  G3C_REQUIRE(depth && out && b > 0 && H > 0 && W > 0, "reliable_depth_mask: bad arguments");
+  G3C_REQUIRE(window % 2 == 1, "Window size must be odd.");
+  k_reliable_mask<<<px_grid(H * W, b), 256, 0, (cudaStream_t)stream>>>(depth, H, W, window,
+                                                                       ratio_thresh, eps, out);
+  G3C_CUDA(cudaGetLastError());
+  return G3C_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+"""ORACLE (test infrastructure only) — seeded synthetic inputs shared by oracle/make_golden.py, the
+tests and bench.py.  No reference dependency; numpy / torch CPU only."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .dit_oracle import DitCfg
+
+F32 = np.float32
+
+
+# --------------------------------------------------------------------------------------------------
+# Path R known-answer cases (SURVEY.md §8c KAT-R1..R5, §8d config 1)
+# --------------------------------------------------------------------------------------------------
+def smooth_depth(h: int, w: int) -> np.ndarray:
+    y, x = np.meshgrid(np.linspace(0, 1, h, dtype=F32), np.linspace(0, 1, w, dtype=F32), indexing="ij")
+    return (2 + np.sin(3 * x) + 0.5 * np.cos(4 * y)).astype(F32)
+
+
+def intrinsics(h: int, w: int, f: float | None = None) -> np.ndarray:
+    f = f if f is not None else 200.0 * w / 256.0
+    return np.array([[f, 0, w / 2], [0, f, h / 2], [0, 0, 1]], dtype=F32)
+
+
+def warp_case(name: str):
+    """Returns dict(depth (b,1,h,w), image (b,3,h,w), mask|None, w2c_src (b,4,4), K (b,3,3), w2c_tgt (b,4,4))."""
+    rng = np.random.RandomState({"R1": 0, "R2": 1, "R3": 2, "R4": 3, "R5": 4, "R6": 5}[name])
+    eye = np.eye(4, dtype=F32)
+    if name in ("R1", "R2"):  # 256x256 identity / 0.1 left pan
+        h = w = 256
+        depth = smooth_depth(h, w)[None, None]
+        img = rng.uniform(-1, 1, (1, 3, h, w)).astype(F32)
+        tgt = eye.copy()
+        if name == "R2":
+            tgt[0, 3] = 0.1
+        return dict(depth=depth, image=img, mask=None, w2c_src=eye[None], K=intrinsics(h, w)[None], w2c_tgt=tgt[None])
+    h, w = 96, 128
+    K = intrinsics(h, w, 100.0)
+    if name == "R3":  # chunk-of-2 coupling: two different target poses in one call
+        depth = np.stack([smooth_depth(h, w), 1.5 * smooth_depth(h, w)])[:, None]
+        img = rng.uniform(-1, 1, (2, 3, h, w)).astype(F32)
+        t0, t1 = eye.copy(), eye.copy()
+        t0[0, 3], t1[2, 3] = -0.05, 0.4
+        return dict(depth=depth, image=img, mask=None, w2c_src=np.stack([eye, eye]), K=np.stack([K, K]),
+                    w2c_tgt=np.stack([t0, t1]))
+    if name == "R4":  # behind-camera points: camera moved forward past part of the scene, with a mask
+        depth = (0.3 + 1.7 * smooth_depth(h, w) / 3.5)[None, None].astype(F32)
+        img = rng.uniform(-1, 1, (1, 3, h, w)).astype(F32)
+        mask = (rng.uniform(0, 1, (1, 1, h, w)) > 0.2).astype(F32)
+        tgt = eye.copy()
+        tgt[2, 3] = -1.0
+        return dict(depth=depth, image=img, mask=mask, w2c_src=eye[None], K=K[None], w2c_tgt=tgt[None])
+    if name == "R5":  # integer coordinates: constant depth, shift by exactly 2 px (f*tx/z = 100*0.04/2)
+        depth = np.full((1, 1, h, w), 2.0, dtype=F32)
+        img = rng.uniform(-1, 1, (1, 3, h, w)).astype(F32)
+        tgt = eye.copy()
+        tgt[0, 3] = 0.04
+        return dict(depth=depth, image=img, mask=None, w2c_src=eye[None], K=K[None], w2c_tgt=tgt[None])
+    if name == "R6":  # rotation + translation, non-identity source pose
+        depth = smooth_depth(h, w)[None, None]
+        img = rng.uniform(-1, 1, (1, 3, h, w)).astype(F32)
+        a = 0.08
+        rot = np.array([[np.cos(a), 0, np.sin(a), 0.1], [0, 1, 0, -0.02], [-np.sin(a), 0, np.cos(a), 0.05],
+                        [0, 0, 0, 1]], dtype=F32)
+        src = eye.copy()
+        src[1, 3] = 0.03
+        return dict(depth=depth, image=img, mask=None, w2c_src=src[None], K=K[None], w2c_tgt=rot[None])
+    raise KeyError(name)
+
+
+def pan_trajectory(n: int, distance: float = 0.3) -> np.ndarray:
+    """n world-to-camera matrices translating along +x (a 'left' pan of the camera)."""
+    out = np.tile(np.eye(4, dtype=F32), (n, 1, 1))
+    out[:, 0, 3] = np.linspace(0, distance, n, dtype=F32)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# Path D cases
+# --------------------------------------------------------------------------------------------------
+TINY = DitCfg(model_channels=256, num_blocks=2, num_heads=2, ffn_dim=1024, context_dim=64, adaln_lora_dim=32,
+              in_channels=81, out_channels=16, concat_padding_mask=True, max_frames=16, max_h=32, max_w=32,
+              rope_t_ratio=2.0)
+TINY_SHAPE = dict(T=2, H=16, W=16, ctx_len=128)  # L = 2*8*8 = 128 tokens
+
+
+def dit_inputs(cfg: DitCfg, T: int, H: int, W: int, ctx_len: int, seed: int = 1, x_scale: float = 1.0):
+    """bf16-representable fp32 tensors: x, cond_mask, cond_pose, padding_mask, ctx (cond/uncond), timestep."""
+    g = torch.Generator().manual_seed(seed)
+
+    def r(*shape, s=1.0):
+        return (s * torch.randn(*shape, generator=g)).to(torch.bfloat16).float()
+
+    x = r(16, T, H, W, s=x_scale)
+    cond_mask = torch.zeros(1, T, H, W)
+    cond_mask[:, 0] = 1.0
+    pose = r(cfg.in_channels - 17, T, H, W, s=0.5)
+    padding = torch.zeros(H, W)
+    ctx_c = r(ctx_len, cfg.context_dim)
+    ctx_u = r(ctx_len, cfg.context_dim)
+    gt = r(16, T, H, W, s=0.5)
+    timestep = float(torch.tensor(0.734375))  # exactly representable in bf16
+    return dict(x=x, cond_mask=cond_mask, pose=pose, padding=padding, ctx_c=ctx_c, ctx_u=ctx_u, gt=gt,
+                timestep=timestep)

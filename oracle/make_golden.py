@@ -1,0 +1,160 @@
+"""Mint the golden vectors under tests/golden/ by executing the REFERENCE'S OWN code (imported from
+/root/reference through oracle/ref_stubs.py) on the seeded cases of oracle/cases.py, and check the
+restated oracles (oracle/warp_oracle.py, oracle/dit_oracle.py) against it while doing so.
+
+Run in the build container only:   python -m oracle.make_golden
+The reference ships no golden vectors for either hot path; these fixtures are the pins.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import cases, dit_oracle, ref_stubs, warp_oracle
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def mint_warp():
+    ref = ref_stubs.reference_warp_module()
+    report = []
+    for name in ("R1", "R2", "R3", "R4", "R5", "R6"):
+        c = cases.warp_case(name)
+        with torch.no_grad():
+            pts = ref.unproject_points(t(c["depth"]), t(c["w2c_src"]), t(c["K"]), is_depth=True)
+            warped, mask, depth, flow = ref.forward_warp(
+                t(c["image"]), None if c["mask"] is None else t(c["mask"]), None, None, t(c["w2c_tgt"]),
+                t(c["K"]), t(c["K"]), render_depth=True, world_points1=pts)
+        pts_o = warp_oracle.unproject_points(c["depth"], c["w2c_src"], c["K"])
+        # feed the oracle the reference's points so that the splat is compared on identical inputs
+        w_o, m_o, d_o, f_o = warp_oracle.forward_warp(c["image"], c["mask"], pts.numpy(), c["w2c_tgt"], c["K"],
+                                                      render_depth=True)
+        e_pts = float(np.abs(pts_o - pts.numpy()).max())
+        e_img = float(np.abs(w_o - warped.numpy()).max())
+        e_msk = float(np.abs(m_o - mask.numpy()).max())
+        e_dep = float(np.abs(d_o - depth.numpy()).max())
+        e_flow = float(np.abs(f_o - flow.numpy()).max())
+        # integer indices on the reference's own flow: must be bit-exact
+        _, fl, ce = warp_oracle.splat_indices(flow.numpy())
+        b, _, h, w = flow.shape
+        grid = ref.create_grid(b, h, w)
+        pos = flow + grid + 1
+        rfl = torch.floor(pos).long()
+        rce = torch.ceil(pos).long()
+        lim = torch.tensor([w + 1, h + 1]).view(1, 2, 1, 1)
+        rfl = torch.minimum(torch.clamp(rfl, min=0), lim)
+        rce = torch.minimum(torch.clamp(rce, min=0), lim)
+        idx_equal = bool((t(fl) == rfl).all() and (t(ce) == rce).all())
+        report.append((name, e_pts, e_img, e_msk, e_dep, e_flow, idx_equal, float(mask.mean())))
+        np.savez_compressed(os.path.join(OUT, f"warp_{name}.npz"), points=pts.numpy(), warped=warped.numpy(),
+                            mask=mask.numpy(), depth=depth.numpy(), flow=flow.numpy(),
+                            floor=rfl.numpy().astype(np.int32), ceil=rce.numpy().astype(np.int32))
+    # reliability mask + render_cache chunking through the reference's Cache3D_Buffer (N = 2 buffers)
+    cache_mod = ref_stubs.reference_cache_module()
+    c = cases.warp_case("R3")
+    F = 3
+    w2cs = t(cases.pan_trajectory(F, 0.1))[None]
+    Ks = t(np.tile(c["K"][:1], (F, 1, 1)))[None]
+    cache = cache_mod.Cache3D_Buffer(
+        frame_buffer_max=2, noise_aug_strength=0, generator=None,
+        input_image=t(c["image"])[None], input_depth=t(c["depth"])[None], input_w2c=t(c["w2c_src"])[None],
+        input_intrinsics=t(c["K"])[None], input_format=["B", "N", "C", "H", "W"], device="cpu",
+        filter_points_threshold=0.05, foreground_masking=False)
+    with torch.no_grad():
+        pix, msk = cache_mod.Cache3D_Base.render_cache(cache, w2cs, Ks)
+    rel = ref.reliable_depth_mask_range_batch(t(c["depth"]).reshape(-1, 1, 96, 128), ratio_thresh=0.05)
+    rel_o = warp_oracle.reliable_depth_mask_range_batch(c["depth"].reshape(-1, 1, 96, 128), ratio_thresh=0.05)
+    pts2 = cache.input_points.numpy()[:, :, :, 0]
+    img2 = cache.input_image.numpy()[:, :, :, 0]
+    m2 = cache.input_mask.numpy()[:, :, :, 0].astype(np.float32)
+    pix_o, msk_o = warp_oracle.render_cache(pts2, img2, m2, w2cs.numpy(), Ks.numpy())
+    e_cache = float(np.abs(pix_o - pix.numpy()).max())
+    np.savez_compressed(os.path.join(OUT, "warp_cache.npz"), pixels=pix.numpy(), masks=msk.numpy(),
+                        reliable=rel.numpy(), points=pts2, cache_mask=m2)
+    print("== Path R: restated oracle vs reference (max abs err) ==")
+    for r in report:
+        print("  %s  points %.2e  image %.2e  mask %.1f  depth %.2e  flow %.2e  indices_bit_exact=%s  coverage %.3f" % r)
+    print("  render_cache(N=2, F=3, chunk 2): image %.2e ; reliable-mask equal: %s" %
+          (e_cache, bool((rel.numpy() == rel_o).all())))
+    bad = [r for r in report if r[2] > 2e-3 or not r[6] or r[3] > 0]
+    if bad or e_cache > 2e-3:
+        print("!! restated warp oracle disagrees with the reference:", bad, e_cache)
+        return 1
+    return 0
+
+
+def mint_dit():
+    Net = ref_stubs.reference_dit_class()
+    from cosmos_predict1.diffusion.conditioner import DataType
+
+    cfg, shp = cases.TINY, cases.TINY_SHAPE
+    net = Net(max_img_h=cfg.max_h * 2, max_img_w=cfg.max_w * 2, max_frames=cfg.max_frames, in_channels=cfg.in_channels,
+              out_channels=cfg.out_channels, patch_spatial=2, patch_temporal=1, model_channels=cfg.model_channels,
+              block_config="FA-CA-MLP", num_blocks=cfg.num_blocks, num_heads=cfg.num_heads, concat_padding_mask=True,
+              pos_emb_cls="rope3d", pos_emb_learnable=False, pos_emb_interpolation="crop", block_x_format="THWBD",
+              affline_emb_norm=True, use_adaln_lora=True, adaln_lora_dim=cfg.adaln_lora_dim,
+              rope_t_extrapolation_ratio=cfg.rope_t_ratio, crossattn_emb_channels=cfg.context_dim)
+    sd = dit_oracle.random_state_dict(cfg, seed=0)
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all("_extra_state" in m for m in missing), missing
+    net.eval()
+    inp = cases.dit_inputs(cfg, **shp)
+
+    def run(net, dtype, pose, ctx):
+        kw = dict(
+            x=inp["x"][None].to(dtype), timesteps=torch.tensor([inp["timestep"]], dtype=dtype),
+            crossattn_emb=ctx[None].to(dtype), crossattn_mask=None, fps=torch.tensor([24.0]),
+            image_size=None, padding_mask=inp["padding"][None, None].to(dtype), data_type=DataType.VIDEO,
+            condition_video_input_mask=inp["cond_mask"][None].to(dtype),
+            condition_video_indicator=torch.zeros(1, 1, shp["T"], 1, 1, dtype=dtype),
+            condition_video_pose=pose[None].to(dtype))
+        with torch.no_grad():
+            return net(**kw)[0].float()
+
+    out_c = run(net, torch.float32, inp["pose"], inp["ctx_c"])
+    out_u = run(net, torch.float32, torch.zeros_like(inp["pose"]), inp["ctx_u"])
+    o_c = dit_oracle.forward(sd, cfg, inp["x"], inp["cond_mask"], inp["pose"], inp["padding"], inp["timestep"], inp["ctx_c"])
+    o_u = dit_oracle.forward(sd, cfg, inp["x"], inp["cond_mask"], None, inp["padding"], inp["timestep"], inp["ctx_u"])
+
+    def rel(a, b):
+        return float((a - b).norm() / b.norm())
+
+    e_c, e_u = rel(o_c, out_c), rel(o_u, out_u)
+    # the reference's own bf16 noise floor (same graph, bf16 weights + activations) vs its fp32 run
+    net_bf = Net(max_img_h=cfg.max_h * 2, max_img_w=cfg.max_w * 2, max_frames=cfg.max_frames, in_channels=cfg.in_channels,
+                 out_channels=cfg.out_channels, patch_spatial=2, patch_temporal=1, model_channels=cfg.model_channels,
+                 block_config="FA-CA-MLP", num_blocks=cfg.num_blocks, num_heads=cfg.num_heads, concat_padding_mask=True,
+                 pos_emb_cls="rope3d", pos_emb_learnable=False, pos_emb_interpolation="crop", block_x_format="THWBD",
+                 affline_emb_norm=True, use_adaln_lora=True, adaln_lora_dim=cfg.adaln_lora_dim,
+                 rope_t_extrapolation_ratio=cfg.rope_t_ratio, crossattn_emb_channels=cfg.context_dim)
+    net_bf.load_state_dict(sd, strict=False)
+    net_bf = net_bf.to(torch.bfloat16).eval()
+    out_c_bf = run(net_bf, torch.bfloat16, inp["pose"], inp["ctx_c"])
+    floor = rel(out_c_bf, out_c)
+    np.savez_compressed(os.path.join(OUT, "dit_tiny.npz"), out_cond=out_c.numpy(), out_uncond=out_u.numpy(),
+                        ref_bf16_rel_l2=np.float32(floor))
+    print("== Path D (tiny 2-block, D=256, L=128): restated oracle vs reference fp32 forward ==")
+    print("  rel-L2 cond %.2e  uncond %.2e ; reference bf16-vs-fp32 noise floor rel-L2 %.2e" % (e_c, e_u, floor))
+    if e_c > 1e-4 or e_u > 1e-4:
+        print("!! restated DiT oracle disagrees with the reference")
+        return 1
+    return 0
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    rc = mint_warp()
+    rc |= mint_dit()
+    sys.exit(rc)
+
+
+if __name__ == "__main__":
+    main()
