@@ -89,6 +89,8 @@ SIGNATURES = {
     "g3c_dit_set_shape": (_I, [_P, _I, _I, _I, _I, _F]),
     "g3c_dit_forward": (_I, [_P, _P, _P, _P, _P, _F, _P, _P, _P]),
     "g3c_denoise_step": (_I, [_P, C.POINTER(StepArgs), _P]),
+    "g3c_dit_profile": (_I, [_P, _I]),
+    "g3c_dit_profile_read": (_I, [_P, C.POINTER(_F), C.POINTER(_I), _I]),
     "g3c_dit_workspace_bytes": (C.c_int64, [_P]),
     "g3c_dit_last_launch_count": (_I, [_P]),
 }

@@ -121,6 +121,11 @@ struct g3c_dit {
   __nv_bfloat16 *lat_xtilde = nullptr, *lat_xin = nullptr, *lat_oc = nullptr, *lat_ou = nullptr;
   bool tables_ready = false;
   int launches = 0;
+  // optional per-category device timing (bench.py roofline): events around every launch
+  bool prof = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_cat;  // category of pair i (events 2i, 2i+1)
+  size_t ev_used = 0;
 };
 
 namespace g3c {
@@ -157,6 +162,28 @@ static int need_bf16(const g3c_dit* h, const std::string& name, std::initializer
   do {                    \
     int _rc = (x);        \
     if (_rc) return _rc;  \
+  } while (0)
+
+enum { CAT_GEMM = 0, CAT_ATTN_SELF = 1, CAT_ATTN_CROSS = 2, CAT_ELTWISE = 3, CAT_COMM = 4, CAT_VECTOR = 5, CAT_N = 6 };
+
+static int prof_mark(g3c_dit* h, int cat, bool begin, cudaStream_t st) {
+  if (!h->prof) return G3C_OK;
+  if (h->ev_used >= h->ev_pool.size()) {
+    cudaEvent_t e;
+    G3C_CUDA(cudaEventCreate(&e));
+    h->ev_pool.push_back(e);
+  }
+  G3C_CUDA(cudaEventRecord(h->ev_pool[h->ev_used++], st));
+  if (begin) h->ev_cat.push_back(cat);
+  return G3C_OK;
+}
+// K(category, launch): count the launch and, in profiling mode, bracket it with events
+#define K(cat, call)                    \
+  do {                                  \
+    TRY(prof_mark(h, cat, true, st));   \
+    TRY(call);                          \
+    TRY(prof_mark(h, cat, false, st));  \
+    ++n;                                \
   } while (0)
 
 static int resolve(g3c_dit* h, cudaStream_t st) {
@@ -258,22 +285,22 @@ static int forward(g3c_dit* h, const void* x_in, const void* cond_mask, const vo
   src.ptr[1] = (const __nv_bfloat16*)cond_mask;   src.nch[1] = 1;                       src.per_frame[1] = 1;
   src.ptr[2] = (const __nv_bfloat16*)cond_pose;   src.nch[2] = c.in_channels - 17;      src.per_frame[2] = 1;
   src.ptr[3] = (const __nv_bfloat16*)padding_mask; src.nch[3] = c.concat_padding_mask ? 1 : 0; src.per_frame[3] = 0;
-  TRY(patchify(src, h->T, h->Hp, h->Wp, h->Kpad, h->tok, st)); ++n;
-  TRY(gemm_bf16(h->tok, h->w_patch_pad, h->x, L, D, h->Kpad, h->Kpad, h->Kpad, D, G3C_EPI_F32, nullptr, 0, st)); ++n;
+  K(CAT_ELTWISE, patchify(src, h->T, h->Hp, h->Wp, h->Kpad, h->tok, st));
+  K(CAT_GEMM, gemm_bf16(h->tok, h->w_patch_pad, h->x, L, D, h->Kpad, h->Kpad, h->Kpad, D, G3C_EPI_F32, nullptr, 0, st));
 
   // ---- timestep embedding + all adaLN-LoRA modulation vectors (blocks.py:38-80, :442-445;
   //      general_dit.py:405).  They depend on t only.
-  TRY(timestep_embed(timestep, D, h->affine_gamma, 1e-6f, h->vec_s, h->vec_emb, st)); ++n;
-  TRY(gemv(h->w_t1, h->vec_s, nullptr, h->vec_h1, D, D, 0, 0, st)); ++n;
-  TRY(gemv(h->w_t2, h->vec_h1, nullptr, h->vec_lora, 3 * D, D, 1, 0, st)); ++n;
+  K(CAT_VECTOR, timestep_embed(timestep, D, h->affine_gamma, 1e-6f, h->vec_s, h->vec_emb, st));
+  K(CAT_VECTOR, gemv(h->w_t1, h->vec_s, nullptr, h->vec_h1, D, D, 0, 0, st));
+  K(CAT_VECTOR, gemv(h->w_t2, h->vec_h1, nullptr, h->vec_lora, 3 * D, D, 1, 0, st));
   for (int i = 0; i < c.num_blocks; ++i)
     for (int j = 0; j < 3; ++j) {
       const SubBlock& s = h->blk[i][j];
-      TRY(gemv(s.ada1, h->vec_emb, nullptr, h->vec_a, R, D, 1, 0, st)); ++n;
-      TRY(gemv(s.ada2, h->vec_a, h->vec_lora, h->mods + (size_t)(i * 3 + j) * 3 * D, 3 * D, R, 0, 0, st)); ++n;
+      K(CAT_VECTOR, gemv(s.ada1, h->vec_emb, nullptr, h->vec_a, R, D, 1, 0, st));
+      K(CAT_VECTOR, gemv(s.ada2, h->vec_a, h->vec_lora, h->mods + (size_t)(i * 3 + j) * 3 * D, 3 * D, R, 0, 0, st));
     }
-  TRY(gemv(h->f_ada1, h->vec_emb, nullptr, h->vec_a, R, D, 1, 0, st)); ++n;
-  TRY(gemv(h->f_ada2, h->vec_a, h->vec_lora, h->modf, 2 * D, R, 0, 0, st)); ++n;
+  K(CAT_VECTOR, gemv(h->f_ada1, h->vec_emb, nullptr, h->vec_a, R, D, 1, 0, st));
+  K(CAT_VECTOR, gemv(h->f_ada2, h->vec_a, h->vec_lora, h->modf, 2 * D, R, 0, 0, st));
 
   __nv_bfloat16* k_loc = h->k_all + (size_t)h->cp_rank * L * D;
   __nv_bfloat16* vt_loc = h->vt_all + (size_t)h->cp_rank * L * D;
@@ -283,10 +310,10 @@ static int forward(g3c_dit* h, const void* x_in, const void* cond_mask, const vo
     {
       const SubBlock& s = h->blk[i][0];
       const float* m = h->mods + (size_t)(i * 3 + 0) * 3 * D;
-      TRY(ln_modulate(h->x, h->pos, m, m + D, h->xn, L, D, 1e-6f, st)); ++n;   // + abs-pos add
-      TRY(gemm_bf16(h->xn, s.wk, k_loc, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st)); ++n;
-      TRY(rmsnorm_rope(k_loc, D, L, heads, s.gk, h->rope, 1e-6f, st)); ++n;
-      TRY(gemm_bf16(s.wv, h->xn, vt_loc, D, L, D, D, D, L, G3C_EPI_BF16, nullptr, 0, st)); ++n;  // V^T
+      K(CAT_ELTWISE, ln_modulate(h->x, h->pos, m, m + D, h->xn, L, D, 1e-6f, st));   // + abs-pos add
+      K(CAT_GEMM, gemm_bf16(h->xn, s.wk, k_loc, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
+      K(CAT_ELTWISE, rmsnorm_rope(k_loc, D, L, heads, s.gk, h->rope, 1e-6f, st));
+      K(CAT_GEMM, gemm_bf16(s.wv, h->xn, vt_loc, D, L, D, D, D, L, G3C_EPI_BF16, nullptr, 0, st));  // V^T
       if (h->cp_size > 1) {
         // one in-place all-gather of K and of V^T per layer, overlapped with the Q projection
         G3C_CUDA(cudaEventRecord(h->ev_kv, st));
@@ -298,40 +325,40 @@ static int forward(g3c_dit* h, const void* x_in, const void* cond_mask, const vo
         G3C_CUDA(cudaEventRecord(h->ev_gathered, h->comm_stream));
         n += 2;
       }
-      TRY(gemm_bf16(h->xn, s.wq, h->q, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st)); ++n;
-      TRY(rmsnorm_rope(h->q, D, L, heads, s.gq, h->rope, 1e-6f, st)); ++n;
+      K(CAT_GEMM, gemm_bf16(h->xn, s.wq, h->q, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
+      K(CAT_ELTWISE, rmsnorm_rope(h->q, D, L, heads, s.gq, h->rope, 1e-6f, st));
       if (h->cp_size > 1) G3C_CUDA(cudaStreamWaitEvent(st, h->ev_gathered, 0));
-      TRY(attn_fwd(h->q, h->k_all, h->vt_all, h->att, L, Lk_all, heads, D, D, D, L, attn_scale, st)); ++n;
-      TRY(gemm_bf16(h->att, s.wo, h->x, L, D, D, D, D, D, G3C_EPI_GATED_RESIDUAL_F32, m + 2 * D, 0, st)); ++n;
+      K(CAT_ATTN_SELF, attn_fwd(h->q, h->k_all, h->vt_all, h->att, L, Lk_all, heads, D, D, D, L, attn_scale, st));
+      K(CAT_GEMM, gemm_bf16(h->att, s.wo, h->x, L, D, D, D, D, D, G3C_EPI_GATED_RESIDUAL_F32, m + 2 * D, 0, st));
     }
     // ---------------- CA: cross-attention to the T5 context (blocks.py:464-471)
     {
       const SubBlock& s = h->blk[i][1];
       const float* m = h->mods + (size_t)(i * 3 + 1) * 3 * D;
       const int C = c.context_dim, M = h->ctx_len;
-      TRY(ln_modulate(h->x, nullptr, m, m + D, h->xn, L, D, 1e-6f, st)); ++n;
-      TRY(gemm_bf16(ctx, s.wk, h->kc, M, D, C, C, C, D, G3C_EPI_BF16, nullptr, 0, st)); ++n;
-      TRY(rmsnorm_rope(h->kc, D, M, heads, s.gk, nullptr, 1e-6f, st)); ++n;
-      TRY(gemm_bf16(s.wv, ctx, h->vtc, D, M, C, C, C, M, G3C_EPI_BF16, nullptr, 0, st)); ++n;
-      TRY(gemm_bf16(h->xn, s.wq, h->q, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st)); ++n;
-      TRY(rmsnorm_rope(h->q, D, L, heads, s.gq, nullptr, 1e-6f, st)); ++n;
-      TRY(attn_fwd(h->q, h->kc, h->vtc, h->att, L, M, heads, D, D, D, M, attn_scale, st)); ++n;
-      TRY(gemm_bf16(h->att, s.wo, h->x, L, D, D, D, D, D, G3C_EPI_GATED_RESIDUAL_F32, m + 2 * D, 0, st)); ++n;
+      K(CAT_ELTWISE, ln_modulate(h->x, nullptr, m, m + D, h->xn, L, D, 1e-6f, st));
+      K(CAT_GEMM, gemm_bf16(ctx, s.wk, h->kc, M, D, C, C, C, D, G3C_EPI_BF16, nullptr, 0, st));
+      K(CAT_ELTWISE, rmsnorm_rope(h->kc, D, M, heads, s.gk, nullptr, 1e-6f, st));
+      K(CAT_GEMM, gemm_bf16(s.wv, ctx, h->vtc, D, M, C, C, C, M, G3C_EPI_BF16, nullptr, 0, st));
+      K(CAT_GEMM, gemm_bf16(h->xn, s.wq, h->q, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
+      K(CAT_ELTWISE, rmsnorm_rope(h->q, D, L, heads, s.gq, nullptr, 1e-6f, st));
+      K(CAT_ATTN_CROSS, attn_fwd(h->q, h->kc, h->vtc, h->att, L, M, heads, D, D, D, M, attn_scale, st));
+      K(CAT_GEMM, gemm_bf16(h->att, s.wo, h->x, L, D, D, D, D, D, G3C_EPI_GATED_RESIDUAL_F32, m + 2 * D, 0, st));
     }
     // ---------------- MLP (attention.py:91-102)
     {
       const SubBlock& s = h->blk[i][2];
       const float* m = h->mods + (size_t)(i * 3 + 2) * 3 * D;
-      TRY(ln_modulate(h->x, nullptr, m, m + D, h->xn, L, D, 1e-6f, st)); ++n;
-      TRY(gemm_bf16(h->xn, s.w1, h->hid, L, F, D, D, D, F, G3C_EPI_GELU_BF16, nullptr, 0, st)); ++n;
-      TRY(gemm_bf16(h->hid, s.w2, h->x, L, D, F, F, F, D, G3C_EPI_GATED_RESIDUAL_F32, m + 2 * D, 0, st)); ++n;
+      K(CAT_ELTWISE, ln_modulate(h->x, nullptr, m, m + D, h->xn, L, D, 1e-6f, st));
+      K(CAT_GEMM, gemm_bf16(h->xn, s.w1, h->hid, L, F, D, D, D, F, G3C_EPI_GELU_BF16, nullptr, 0, st));
+      K(CAT_GEMM, gemm_bf16(h->hid, s.w2, h->x, L, D, F, F, F, D, G3C_EPI_GATED_RESIDUAL_F32, m + 2 * D, 0, st));
     }
   }
   // ---- final layer + unpatchify (blocks.py:222-242, general_dit.py:328-358)
   const int No = c.out_channels * 4;
-  TRY(ln_modulate(h->x, nullptr, h->modf, h->modf + D, h->xn, L, D, 1e-6f, st)); ++n;
-  TRY(gemm_bf16(h->xn, h->w_final, h->yfin, L, No, D, D, D, No, G3C_EPI_F32, nullptr, 64, st)); ++n;
-  TRY(unpatchify(h->yfin, No, h->T, h->Hp, h->Wp, c.out_channels, (__nv_bfloat16*)out, st)); ++n;
+  K(CAT_ELTWISE, ln_modulate(h->x, nullptr, h->modf, h->modf + D, h->xn, L, D, 1e-6f, st));
+  K(CAT_GEMM, gemm_bf16(h->xn, h->w_final, h->yfin, L, No, D, D, D, No, G3C_EPI_F32, nullptr, 64, st));
+  K(CAT_ELTWISE, unpatchify(h->yfin, No, h->T, h->Hp, h->Wp, c.out_channels, (__nv_bfloat16*)out, st));
   h->launches = n;
   return G3C_OK;
 }
@@ -371,6 +398,7 @@ int g3c_dit_destroy(g3c_dit_t* h) {
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   if (h->ev_kv) cudaEventDestroy(h->ev_kv);
   if (h->ev_gathered) cudaEventDestroy(h->ev_gathered);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   delete h;
   return G3C_OK;
 }
@@ -521,6 +549,32 @@ int g3c_denoise_step(g3c_dit_t* h, const g3c_step_args* a, void* stream) {
                    16, h->T, plane, a->guidance, a->sigma, a->sigma_next, a->sigma_aug, a->sigma_data,
                    (__nv_bfloat16*)a->xt_next, st));
   h->launches += n1 + 2;
+  return G3C_OK;
+}
+
+int g3c_dit_profile(g3c_dit_t* h, int enable) {
+  G3C_REQUIRE(h, "dit_profile: null handle");
+  h->prof = enable != 0;
+  h->ev_used = 0;
+  h->ev_cat.clear();
+  return G3C_OK;
+}
+
+int g3c_dit_profile_read(g3c_dit_t* h, float* ms_by_category, int* launches_by_category, int ncat) {
+  G3C_REQUIRE(h && ms_by_category && launches_by_category && ncat >= CAT_N, "dit_profile_read: need %d categories", CAT_N);
+  for (int i = 0; i < ncat; ++i) {
+    ms_by_category[i] = 0.f;
+    launches_by_category[i] = 0;
+  }
+  G3C_CUDA(cudaDeviceSynchronize());
+  for (size_t i = 0; i < h->ev_cat.size() && 2 * i + 1 < h->ev_used; ++i) {
+    float ms = 0.f;
+    G3C_CUDA(cudaEventElapsedTime(&ms, h->ev_pool[2 * i], h->ev_pool[2 * i + 1]));
+    ms_by_category[h->ev_cat[i]] += ms;
+    launches_by_category[h->ev_cat[i]] += 1;
+  }
+  h->ev_used = 0;
+  h->ev_cat.clear();
   return G3C_OK;
 }
 

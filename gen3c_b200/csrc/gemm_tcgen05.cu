@@ -38,7 +38,8 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarBytes = 256;
-  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+  static constexpr int kStageF32 = 4 * 32 * 33 * 4;  // epilogue transpose buffers (fp32 outputs)
+  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + kStageF32 + 1024;  // + alignment slack
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   uint64_t* tfull = bars + 2 * kStages;     // [2]
   uint64_t* tempty = bars + 2 * kStages + 2;  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  float* stage_f32 = reinterpret_cast<float*>(smem + kStages * S::kStageBytes + S::kBarBytes);
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -177,9 +179,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         tmem_ld32(tmem_base + ((ew * 32u) << 16) + as * BN + c * 32, r);
         tc_wait_ld();
         const int col0 = n_blk * BN + c * 32;
-        if (row_ok && col0 < p.N) {
-          const bool full_chunk = col0 + 32 <= p.N;
-          if constexpr (EPI == G3C_EPI_BF16 || EPI == G3C_EPI_GELU_BF16) {
+        if constexpr (EPI == G3C_EPI_BF16 || EPI == G3C_EPI_GELU_BF16) {
+          // lane = row: each thread stores 64 contiguous bytes of its own row (full 32-B sectors)
+          if (row_ok && col0 < p.N) {
+            const bool full_chunk = col0 + 32 <= p.N;
             __nv_bfloat16* dptr = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col0;
             float v[32];
 #pragma unroll
@@ -202,31 +205,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               for (int i = 0; i < 32; ++i)
                 if (col0 + i < p.N) dptr[i] = __float2bfloat16_rn(v[i]);
             }
-          } else {
-            float* dptr = reinterpret_cast<float*>(p.D) + (size_t)row * p.ldd + col0;
-            if (full_chunk) {
+          }
+        } else {
+          // fp32 output / gated residual: transpose the 32x32 chunk through shared memory so that every
+          // global access of the warp is one contiguous 128-byte row segment (lane = column).
+          if (col0 < p.N) {  // warp-uniform
+            float* stg = stage_f32 + ew * (32 * 33);
+            __syncwarp();
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float4 acc = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                         __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-                if constexpr (EPI == G3C_EPI_GATED_RESIDUAL_F32) {
-                  float4 g = *reinterpret_cast<const float4*>(p.gate + col0 + 4 * i);
-                  float4 x = reinterpret_cast<float4*>(dptr)[i];
-                  acc.x = fmaf(g.x, acc.x, x.x);
-                  acc.y = fmaf(g.y, acc.y, x.y);
-                  acc.z = fmaf(g.z, acc.z, x.z);
-                  acc.w = fmaf(g.w, acc.w, x.w);
-                }
-                reinterpret_cast<float4*>(dptr)[i] = acc;
+            for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(r[i]);
+            __syncwarp();
+            const int col = col0 + lane;
+            const bool col_ok = col < p.N;
+            const int row0 = m_blk * BM + ew * 32;
+            float g = 0.0f;
+            if constexpr (EPI == G3C_EPI_GATED_RESIDUAL_F32) g = col_ok ? p.gate[col] : 0.0f;
+            float* dbase = reinterpret_cast<float*>(p.D) + (size_t)row0 * p.ldd + col;
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+              float xv[8];
+              if constexpr (EPI == G3C_EPI_GATED_RESIDUAL_F32) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  xv[j] = (col_ok && row0 + r0 + j < p.M) ? dbase[(size_t)(r0 + j) * p.ldd] : 0.0f;
               }
-            } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                if (col0 + i < p.N) {
-                  float a = __uint_as_float(r[i]);
-                  if constexpr (EPI == G3C_EPI_GATED_RESIDUAL_F32) a = fmaf(p.gate[col0 + i], a, dptr[i]);
-                  dptr[i] = a;
-                }
+              for (int j = 0; j < 8; ++j) {
+                float a = stg[(r0 + j) * 33 + lane];
+                if constexpr (EPI == G3C_EPI_GATED_RESIDUAL_F32) a = fmaf(g, a, xv[j]);
+                if (col_ok && row0 + r0 + j < p.M) dbase[(size_t)(r0 + j) * p.ldd] = a;
               }
             }
           }

@@ -182,6 +182,14 @@ typedef struct g3c_step_args {
  * :249-259 and the EDM Euler step of diffusers 0.32.2): two DiT forwards + sampler glue. */
 int g3c_denoise_step(g3c_dit_t* h, const g3c_step_args* a, void* stream);
 
+/* Device-side timing by kernel category for bench.py's roofline: with profiling enabled every launch
+ * of g3c_dit_forward is bracketed by CUDA events on the launching stream.  Categories:
+ * 0 GEMM, 1 self-attention, 2 cross-attention, 3 elementwise, 4 comm, 5 B=1 vector ops.
+ * g3c_dit_profile_read synchronises, sums elapsed ms / launch counts per category and resets. */
+#define G3C_PROFILE_CATEGORIES 6
+int g3c_dit_profile(g3c_dit_t* h, int enable);
+int g3c_dit_profile_read(g3c_dit_t* h, float* ms_by_category, int* launches_by_category, int ncat);
+
 /* bytes of device workspace currently held by the handle */
 int64_t g3c_dit_workspace_bytes(const g3c_dit_t* h);
 /* number of kernels the last g3c_dit_forward enqueued (for bench.py's gpu_launches) */

@@ -40,8 +40,10 @@ def warp_case(name: str):
     if name == "R3":  # chunk-of-2 coupling: two different target poses in one call
         depth = np.stack([smooth_depth(h, w), 1.5 * smooth_depth(h, w)])[:, None]
         img = rng.uniform(-1, 1, (2, 3, h, w)).astype(F32)
-        t0, t1 = eye.copy(), eye.copy()
-        t0[0, 3], t1[2, 3] = -0.05, 0.4
+        # generic poses (yaw + pitch + translation): a pure axis-aligned pan puts every y coordinate
+        # within 1 ulp of an integer, where floor/ceil of the reference algorithm flip with the rounding
+        # order of the projection (a x2 change of that source's weight) - see DESIGN.md section 2.
+        t0, t1 = look(0.03, -0.02, (-0.05, 0.01, 0.02)), look(-0.02, 0.015, (0.02, -0.01, 0.4))
         return dict(depth=depth, image=img, mask=None, w2c_src=np.stack([eye, eye]), K=np.stack([K, K]),
                     w2c_tgt=np.stack([t0, t1]))
     if name == "R4":  # behind-camera points: camera moved forward past part of the scene, with a mask
@@ -69,11 +71,25 @@ def warp_case(name: str):
     raise KeyError(name)
 
 
+def look(yaw: float, pitch: float, t) -> np.ndarray:
+    """world-to-camera matrix: rotation yaw (about y) then pitch (about x), translation t."""
+    cy, sy, cp, sp = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch)
+    ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    rx = np.array([[1, 0, 0], [0, cp, -sp], [0, sp, cp]])
+    m = np.eye(4)
+    m[:3, :3] = rx @ ry
+    m[:3, 3] = t
+    return m.astype(F32)
+
+
 def pan_trajectory(n: int, distance: float = 0.3) -> np.ndarray:
-    """n world-to-camera matrices translating along +x (a 'left' pan of the camera)."""
-    out = np.tile(np.eye(4, dtype=F32), (n, 1, 1))
-    out[:, 0, 3] = np.linspace(0, distance, n, dtype=F32)
-    return out
+    """n world-to-camera matrices: a 'left' pan (translation along +x) that keeps facing the scene centre
+    (yaw grows with the offset) with a slight pitch, so projected coordinates are generic (non-integer)."""
+    out = []
+    for i in range(n):
+        a = i / max(1, n - 1)
+        out.append(look(-0.12 * a * distance / 0.3 - 0.004, 0.003 + 0.01 * a, (distance * a, 0.002 * a, 0.01 * a)))
+    return np.stack(out).astype(F32)
 
 
 # --------------------------------------------------------------------------------------------------
