@@ -113,7 +113,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = min(os.cpu_count() or 1, 64)  # torch's CPU GEMM/SDPA stop scaling (and regress) beyond this
     cpu_sample_seconds(threads)  # page-in / warm
     for _ in range(max(0, args.warmup - 1)):
         cpu_sample_seconds(threads)
@@ -285,7 +285,7 @@ def run_ours(args):
         "workspace_gb": net.workspace_bytes() / 1e9,
     }
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = min(os.cpu_count() or 1, 64)
         cpu_sample_seconds(threads)
         dt, flops = cpu_sample_seconds(threads)
         line["cpu_baseline"] = {

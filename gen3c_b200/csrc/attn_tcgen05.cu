@@ -21,6 +21,8 @@
 // the whole PV/S pair of the other overlap with that tile's softmax.
 // Online softmax keeps a lazily updated reference max: O / row-sum are only rescaled when the row
 // max grew by more than 2^8, so the TMEM read-modify-write of O is rare after the first tiles.
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace g3c {
@@ -46,6 +48,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, rel. err 7.5e-5, far below the bf16
+// rounding of P): the MUFU unit delivers only 16 ex2/clk/SM, which is exactly as slow as the two MMAs of a
+// KV step; computing every kPolyEvery-th exponential here takes the softmax off the critical path.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float xr = x + 12582912.0f;  // 1.5 * 2^23: low mantissa bits now hold round(x)
+  const float n = xr - 12582912.0f;
+  const float f = x - n;  // [-0.5, 0.5]
+  const float p = fmaf(fmaf(fmaf(0.05517165f, f, 0.24261113f), f, 0.69326097f), f, 0.99992806f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
+
+template <int kPolyEvery>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
     k_attn_fwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -239,8 +254,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         uint32_t pk[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float a = ex2_approx(fmaf(__uint_as_float(s[hh * 64 + 2 * i]), c, neg));
-          float b = ex2_approx(fmaf(__uint_as_float(s[hh * 64 + 2 * i + 1]), c, neg));
+          const float xa = fmaf(__uint_as_float(s[hh * 64 + 2 * i]), c, neg);
+          const float xb = fmaf(__uint_as_float(s[hh * 64 + 2 * i + 1]), c, neg);
+          float a = ex2_approx(xa);
+          float b = (kPolyEvery > 0 && (i % (kPolyEvery / 2 > 0 ? kPolyEvery / 2 : 1)) == 0) ? ex2_poly(xb) : ex2_approx(xb);
           l += a + b;
           pk[i] = pack_bf16x2(a, b);
         }
@@ -316,10 +333,16 @@ int attn_fwd(const void* q, const void* k, const void* vt, void* o, int Lq, int 
     int rc = make_tmap_bf16_sw128(&tmV, vt, 3, dims, str, box);
     if (rc) return rc;
   }
-  static bool configured = false;
-  if (!configured) {
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    configured = true;
+  // fraction of exponentials evaluated on the FMA pipe: 1/kPolyEvery (0 = none); G3C_ATTN_POLY overrides
+  static int poly = -1;
+  if (poly < 0) {
+    const char* e = getenv("G3C_ATTN_POLY");
+    poly = e ? atoi(e) : 4;
+    if (poly != 0 && poly != 2 && poly != 4 && poly != 8) poly = 4;
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
   }
   AttnParams p;
   p.Lq = Lq;
@@ -330,7 +353,12 @@ int attn_fwd(const void* q, const void* k, const void* vt, void* o, int Lq, int 
   p.O = reinterpret_cast<__nv_bfloat16*>(o);
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((Lq + 2 * ATT_TILE - 1) / (2 * ATT_TILE), heads);
-  k_attn_fwd<<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+  switch (poly) {
+    case 0: k_attn_fwd<0><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+    case 2: k_attn_fwd<2><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+    case 8: k_attn_fwd<8><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+    default: k_attn_fwd<4><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+  }
   G3C_CUDA(cudaGetLastError());
   return G3C_OK;
 }

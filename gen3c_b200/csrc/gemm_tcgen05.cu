@@ -13,6 +13,8 @@
 //   warp 2      TMEM allocator
 //   warps 4-7   epilogue       : tcgen05.ld (lane = row) -> fused epilogue -> global
 // Two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cstring>
+
 #include "kernels.h"
 
 namespace g3c {
@@ -38,8 +40,8 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarBytes = 256;
-  static constexpr int kStageF32 = 4 * 32 * 33 * 4;  // epilogue transpose buffers (fp32 outputs)
-  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + kStageF32 + 1024;  // + alignment slack
+  static constexpr int kStageF32 = 4 * 2 * 4096;  // fp32 epilogue: per warp 2 x (32 rows x 128 B) TMA-store tiles
+  static constexpr int kTotal = kStages * kStageBytes + kStageF32 + kBarBytes + 1024;  // + alignment slack
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -67,7 +69,7 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     k_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-           const GemmParams p) {
+           const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
   using S = GemmSmem<BN>;
   constexpr int kStages = S::kStages;
   constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
@@ -77,13 +79,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * S::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint8_t* stage_f32 = smem + kStages * S::kStageBytes;  // 1024-byte aligned (stage bytes are multiples of 1 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_f32 + S::kStageF32);
   uint64_t* full = bars;                    // [kStages]
   uint64_t* empty = bars + kStages;         // [kStages]
   uint64_t* tfull = bars + 2 * kStages;     // [2]
   uint64_t* tempty = bars + 2 * kStages + 2;  // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  float* stage_f32 = reinterpret_cast<float*>(smem + kStages * S::kStageBytes + S::kBarBytes);
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> global =====
     const uint32_t ew = warp - 4;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
-    uint32_t as = 0, aphase = 0;
+    uint32_t as = 0, aphase = 0, ebuf = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
       tile_coords(p, tile, m_blk, n_blk);
@@ -207,35 +209,42 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
             }
           }
         } else {
-          // fp32 output / gated residual: transpose the 32x32 chunk through shared memory so that every
-          // global access of the warp is one contiguous 128-byte row segment (lane = column).
+          // fp32 output / gated residual: the 32x32 fp32 chunk goes to a 128-byte-swizzled shared tile and one
+          // elected lane hands it to the TMA: plain store, or reduce-add into the fp32 residual stream in L2
+          // (x += gate * acc without ever loading x into the SM).  TMA clips rows >= M / columns >= N.
           if (col0 < p.N) {  // warp-uniform
-            float* stg = stage_f32 + ew * (32 * 33);
+            uint8_t* stg = stage_f32 + (ew * 2 + (ebuf & 1)) * 4096;
+            if (lane == 0) tma_store_wait_read<1>();  // the store that last used this buffer has read it
             __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(r[i]);
-            __syncwarp();
-            const int col = col0 + lane;
-            const bool col_ok = col < p.N;
-            const int row0 = m_blk * BM + ew * 32;
-            float g = 0.0f;
-            if constexpr (EPI == G3C_EPI_GATED_RESIDUAL_F32) g = col_ok ? p.gate[col] : 0.0f;
-            float* dbase = reinterpret_cast<float*>(p.D) + (size_t)row0 * p.ldd + col;
-#pragma unroll
-            for (int r0 = 0; r0 < 32; r0 += 8) {
-              float xv[8];
+            for (int j = 0; j < 8; ++j) {
+              float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                     __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
               if constexpr (EPI == G3C_EPI_GATED_RESIDUAL_F32) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  xv[j] = (col_ok && row0 + r0 + j < p.M) ? dbase[(size_t)(r0 + j) * p.ldd] : 0.0f;
+                const int cg = col0 + 4 * j;
+                float4 g;
+                if (cg + 4 <= p.N) {
+                  g = *reinterpret_cast<const float4*>(p.gate + cg);
+                } else {  // ragged right edge: columns >= N are clipped by the TMA
+                  g.x = cg + 0 < p.N ? p.gate[cg + 0] : 0.f;
+                  g.y = cg + 1 < p.N ? p.gate[cg + 1] : 0.f;
+                  g.z = cg + 2 < p.N ? p.gate[cg + 2] : 0.f;
+                  g.w = 0.f;
+                }
+                v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
               }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float a = stg[(r0 + j) * 33 + lane];
-                if constexpr (EPI == G3C_EPI_GATED_RESIDUAL_F32) a = fmaf(g, a, xv[j]);
-                if (col_ok && row0 + r0 + j < p.M) dbase[(size_t)(r0 + j) * p.ldd] = a;
-              }
+              // row = lane, 16-byte chunk j -> swizzled chunk j ^ (row % 8)
+              *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
             }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              const int row0 = m_blk * BM + ew * 32;
+              if constexpr (EPI == G3C_EPI_GATED_RESIDUAL_F32) tma_reduce_add_2d(&tmD, stg, col0, row0);
+              else tma_store_2d(&tmD, stg, col0, row0);
+              tma_store_commit();
+            }
+            ++ebuf;
           }
         }
       }
@@ -246,6 +255,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
         aphase ^= 1;
       }
     }
+    if (lane == 0) tma_store_wait_all<0>();  // all bulk stores of this warp are complete before exit
   }
 
   tc_fence_before();
@@ -257,8 +267,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 }
 
 template <int BN, int EPI>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
-                       cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                       const GemmParams& p, cudaStream_t st) {
   using S = GemmSmem<BN>;
   static bool configured = false;
   if (!configured) {
@@ -268,19 +278,19 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   int tiles = p.num_m_blk * p.num_n_blk;
   int grid = tiles < sm_count() ? tiles : sm_count();
-  k_gemm<BN, EPI><<<grid, GEMM_THREADS, S::kTotal, st>>>(tmA, tmB, p);
+  k_gemm<BN, EPI><<<grid, GEMM_THREADS, S::kTotal, st>>>(tmA, tmB, tmD, p);
   G3C_CUDA(cudaGetLastError());
   return G3C_OK;
 }
 
 template <int BN>
-static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
-                        cudaStream_t st) {
+static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                        const GemmParams& p, cudaStream_t st) {
   switch (epi) {
-    case G3C_EPI_BF16: return launch_gemm<BN, G3C_EPI_BF16>(tmA, tmB, p, st);
-    case G3C_EPI_GELU_BF16: return launch_gemm<BN, G3C_EPI_GELU_BF16>(tmA, tmB, p, st);
-    case G3C_EPI_GATED_RESIDUAL_F32: return launch_gemm<BN, G3C_EPI_GATED_RESIDUAL_F32>(tmA, tmB, p, st);
-    case G3C_EPI_F32: return launch_gemm<BN, G3C_EPI_F32>(tmA, tmB, p, st);
+    case G3C_EPI_BF16: return launch_gemm<BN, G3C_EPI_BF16>(tmA, tmB, tmD, p, st);
+    case G3C_EPI_GELU_BF16: return launch_gemm<BN, G3C_EPI_GELU_BF16>(tmA, tmB, tmD, p, st);
+    case G3C_EPI_GATED_RESIDUAL_F32: return launch_gemm<BN, G3C_EPI_GATED_RESIDUAL_F32>(tmA, tmB, tmD, p, st);
+    case G3C_EPI_F32: return launch_gemm<BN, G3C_EPI_F32>(tmA, tmB, tmD, p, st);
   }
   set_error("gemm: unknown epilogue %d", epi);
   return G3C_EINVAL;
@@ -316,6 +326,15 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int ld
   rc = make_tmap_bf16_sw128(&tmB, B, 2, dimsB, strB, boxB);
   if (rc) return rc;
 
+  CUtensorMap tmD;
+  memset(&tmD, 0, sizeof(tmD));
+  if (epilogue == G3C_EPI_GATED_RESIDUAL_F32 || epilogue == G3C_EPI_F32) {
+    uint64_t dimsD[2] = {(uint64_t)N, (uint64_t)M}, strD[1] = {(uint64_t)ldd * 4};
+    uint32_t boxD[2] = {32, 32};
+    rc = make_tmap_f32_sw128(&tmD, D, dimsD, strD, boxD);
+    if (rc) return rc;
+  }
+
   GemmParams p;
   p.M = M;
   p.N = N;
@@ -333,9 +352,9 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int ld
   if (sn > p.num_n_blk) sn = p.num_n_blk;
   p.super_n = sn;
   switch (bn) {
-    case 64: return dispatch_epi<64>(epilogue, tmA, tmB, p, st);
-    case 128: return dispatch_epi<128>(epilogue, tmA, tmB, p, st);
-    default: return dispatch_epi<256>(epilogue, tmA, tmB, p, st);
+    case 64: return dispatch_epi<64>(epilogue, tmA, tmB, tmD, p, st);
+    case 128: return dispatch_epi<128>(epilogue, tmA, tmB, tmD, p, st);
+    default: return dispatch_epi<256>(epilogue, tmA, tmB, tmD, p, st);
   }
 }
 

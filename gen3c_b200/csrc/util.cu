@@ -85,6 +85,31 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uin
   return G3C_OK;
 }
 
+int make_tmap_f32_sw128(CUtensorMap* out, const void* base, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return G3C_ECUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || strides_bytes[0] % 16 != 0) {
+    set_error("TMA f32 map: base %p / stride %llu not 16-byte aligned", base,
+              (unsigned long long)strides_bytes[0]);
+    return G3C_EINVAL;
+  }
+  cuuint64_t gdims[2] = {dims[0], dims[1]};
+  cuuint64_t gstr[1] = {strides_bytes[0]};
+  cuuint32_t gbox[2] = {box[0], box[1]}, estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdims, gstr, gbox, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(f32) failed with CUresult %d", (int)r);
+    return G3C_ECUDA;
+  }
+  return G3C_OK;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {

@@ -1,0 +1,43 @@
+"""Minimal launch targets for `ncu --set full`: one self-attention, one projection GEMM, one gated GEMM and one
+cache render at BASELINE sizes.  Usage: python tools/ncu_target.py [attn|gemm|warp]"""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from gen3c_b200 import ops, warp  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "attn"
+
+
+def bf(*s, sc=1.0):
+    return (torch.randn(*s, device="cuda") * sc).to(torch.bfloat16)
+
+
+if which == "attn":
+    L, H = 56320, 32
+    q, k, vt = bf(L, H * 128), bf(L, H * 128), bf(H * 128, L)
+    for _ in range(2):
+        o = ops.attention(q, k, vt, H)
+elif which == "gemm":
+    L = 56320
+    a, w = bf(L, 4096), bf(4096, 4096, sc=0.02)
+    x = torch.zeros(L, 4096, device="cuda")
+    gate = torch.ones(4096, device="cuda")
+    for _ in range(2):
+        ops.gemm(a, w, ops.EPI_BF16)
+        ops.gemm(a, w, ops.EPI_GATED_RESIDUAL_F32, out=x, gate=gate)
+elif which == "warp":
+    from oracle import cases
+
+    h, w_, F = 704, 1280, 8
+    depth = torch.from_numpy(cases.smooth_depth(h, w_)[None, None]).cuda()
+    K = torch.from_numpy(cases.intrinsics(h, w_)[None]).cuda()
+    eye = torch.eye(4, device="cuda")[None]
+    img = torch.rand(1, 3, h, w_, device="cuda") * 2 - 1
+    pts = warp.unproject_points(depth, eye, K)
+    w2cs = torch.from_numpy(cases.pan_trajectory(F, 0.3)).cuda()[None]
+    Ks = K[None].expand(1, F, 3, 3).contiguous()
+    for _ in range(2):
+        warp.render_cache(pts[None, None], img[None, None], None, w2cs, Ks, max_items_per_pass=4)
+torch.cuda.synchronize()
