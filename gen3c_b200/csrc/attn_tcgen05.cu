@@ -15,19 +15,25 @@
 //   warps 4-7  softmax of tile B
 //   warp  8    TMA producer: Q once, then K_j / V_j through a 4-slot ring of 32 KB tiles
 //   warp  9    TMEM allocator + single-thread MMA issuer
-// TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,384) O_B [384,512); P (bf16) overwrites
-// the first 64 columns of its S tile and feeds the P·V MMA straight from TMEM.
-// MMA order per KV step j:  PV_A(j) ; S_A(j+1) ; PV_B(j) ; S_B(j+1)  — the S MMA of one tile and
-// the whole PV/S pair of the other overlap with that tile's softmax.
-// Online softmax keeps a lazily updated reference max: O / row-sum are only rescaled when the row
-// max grew by more than 2^8, so the TMEM read-modify-write of O is rare after the first tiles.
+// TMEM (512 columns): S [0,128) — ONE score buffer shared by both tiles —, P_A [128,192), P_B [192,256)
+// (bf16 probabilities, the TMEM A operand of the P·V MMA), O_A [256,384), O_B [384,512).
+// The round-1 profile of the first version (P aliasing a per-tile S buffer, profiles/r01_attn_ncu_summary.txt)
+// showed a strict A/B alternation: QK_X(j+1) could not be issued before PV_X(j) had consumed P_X(j), so each
+// tile paid softmax + MMA + two barrier hops in series (tensor pipe 52-56 %, softmax warps idle ~45 %).
+// Here a softmax thread copies its S row into registers and immediately hands the S buffer back (`s_free`);
+// P lives in its own columns, so the MMA issue order becomes
+//     QK_A(j+1) ; PV_A(j) ; QK_B(j+1) ; PV_B(j)
+// and S_X(j+1) is already waiting in TMEM when softmax X finishes tile j: both softmax warpgroups run back to
+// back (2 warps per SM sub-partition interleave MUFU and FMA work) while the tensor pipe never waits for them.
+// Online softmax keeps a lazily updated reference max: O / row-sum are only rescaled when the row max grew
+// by more than 2^8 (after PV(j-1) has committed), so the TMEM read-modify-write of O is rare.
 #include <cstdlib>
 
 #include "kernels.h"
 
 namespace g3c {
 
-constexpr int ATT_THREADS = 320;
+constexpr int ATT_THREADS = 384;  // 3 warpgroups: softmax A, softmax B, {TMA, MMA, 2 idle}
 constexpr int ATT_TILE = 128;             // rows per Q tile, keys per KV tile, head dim
 constexpr int ATT_HALF_BYTES = 128 * 128; // one 64-column half of a 128x128 bf16 tile
 constexpr int ATT_TILE_BYTES = 2 * ATT_HALF_BYTES;
@@ -44,7 +50,7 @@ struct AttnParams {
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
   return y;
 }
 
@@ -73,9 +79,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
   uint64_t* q_full = bars;                        // [1]
   uint64_t* kv_full = bars + 1;                   // [slots]
   uint64_t* kv_empty = bars + 1 + ATT_SLOTS;      // [slots]
-  uint64_t* s_full = bars + 1 + 2 * ATT_SLOTS;    // [2]
-  uint64_t* p_full = bars + 3 + 2 * ATT_SLOTS;    // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5 + 2 * ATT_SLOTS);
+  uint64_t* s_full = bars + 1 + 2 * ATT_SLOTS;    // [2]  QK_t done          (tcgen05.commit)
+  uint64_t* p_full = bars + 3 + 2 * ATT_SLOTS;    // [2]  P_t stored         (128 softmax threads)
+  uint64_t* pv_done = bars + 5 + 2 * ATT_SLOTS;   // [2]  PV_t done          (tcgen05.commit)
+  uint64_t* s_free = bars + 7 + 2 * ATT_SLOTS;    // [1]  S copied to registers (128 softmax threads)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8 + 2 * ATT_SLOTS);
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -94,8 +102,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], 4);   // one elected arrive per softmax warp
+      mbar_init(&pv_done[i], 1);
     }
+    mbar_init(s_free, 4);
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(tmem_ptr, 512);
@@ -104,8 +114,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 8) {
-    if (lane == 0) {
+  // register budget: the data-movement warpgroup gives its registers to the two softmax warpgroups
+  // register budget: the data-movement warpgroup (warps 8-11) hands registers to the softmax warpgroups.
+  // The pool is what the CTA was launched with (384 x 168): 256 x 208 + 128 x 72 <= 64512.
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
+    if (warp == 8 && lane == 0) {
       // ===== TMA producer =====
       mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
 #pragma unroll
@@ -115,19 +129,19 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           tma_load_2d(smem_q + t * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmQ, q_full,
                       head * 128 + h * 64, q0 + t * ATT_TILE);
       uint32_t slot = 0, phase = 0;
-      for (int j = 0; j < n_kv; ++j) {
-        const int kv0 = j * ATT_TILE;
-        // K_j
+      auto load_k = [&](int j) {
         mbar_wait(&kv_empty[slot], phase ^ 1);
         mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
 #pragma unroll
         for (int h = 0; h < 2; ++h)
           tma_load_2d(smem_kv + slot * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmK, &kv_full[slot],
-                      head * 128 + h * 64, kv0);
+                      head * 128 + h * 64, j * ATT_TILE);
         if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; }
-        // V_j  (transposed: rows = head dim, columns = keys)
+      };
+      auto load_v = [&](int j) {  // transposed: rows = head dim, columns = keys
         mbar_wait(&kv_empty[slot], phase ^ 1);
         mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
+        const int kv0 = j * ATT_TILE;
         const int chunk = kv0 / p.vt_chunk_len;
         const int koff = kv0 - chunk * p.vt_chunk_len;
 #pragma unroll
@@ -135,25 +149,42 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           tma_load_3d(smem_kv + slot * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmV, &kv_full[slot],
                       koff + h * 64, head * 128, chunk);
         if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; }
+      };
+      // consumption order of the MMA warp: K0, then per step j: K_{j+1}, V_j
+      load_k(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) load_k(j + 1);
+        load_v(j);
       }
-    }
-  } else if (warp == 9) {
-    if (lane == 0) {
+    } else if (warp == 9 && lane == 0) {
       // ===== MMA issuer =====
       constexpr uint32_t idesc = make_idesc_bf16(128, 128);
-      const uint32_t tS[2] = {tmem_base, tmem_base + 128};
+      const uint32_t tS = tmem_base;
+      const uint32_t tP[2] = {tmem_base + 128, tmem_base + 192};
       const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
       uint32_t slot = 0, phase = 0;
-      auto advance = [&]() { if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; } };
+      auto take = [&]() {  // next ring slot, once the TMA has filled it
+        mbar_wait(&kv_full[slot], phase);
+        const uint32_t sl = slot;
+        if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; }
+        return sl;
+      };
+      uint32_t n_free = 0;  // how many hand-backs of the S buffer have been consumed
+      auto wait_s_free = [&]() {
+        mbar_wait(s_free, n_free & 1);
+        ++n_free;
+        tc_fence_after();
+      };
       auto mma_s = [&](int t, uint32_t kslot) {
-        // S_t = Q_t K^T : 8 k-steps over the head dimension
+        // S = Q_t K^T : 8 k-steps over the head dimension
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t half = k >> 2, off = (k & 3) * 32;
           uint64_t da = make_sdesc_sw128(smem_u32(smem_q + t * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
           uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + kslot * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
-          umma_ss(tS[t], sdesc_advance(da, off), sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
+          umma_ss(tS, sdesc_advance(da, off), sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
         }
+        umma_commit(&s_full[t]);
       };
       auto mma_pv = [&](int t, uint32_t vslot, bool first) {
         // O_t += P_t V : 8 k-steps over the 128 keys; A = P from TMEM (bf16 pairs per column)
@@ -161,68 +192,68 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         for (int k = 0; k < 8; ++k) {
           const uint32_t half = k >> 2, off = (k & 3) * 32;
           uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + vslot * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
-          umma_ts(tO[t], tS[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
+          umma_ts(tO[t], tP[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
         }
+        umma_commit(&pv_done[t]);
       };
       mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[slot], phase);
+      uint32_t kslot = take();  // K_0
       tc_fence_after();
-      uint32_t kslot = slot;
-      advance();
       mma_s(0, kslot);
-      umma_commit(&s_full[0]);
+      wait_s_free();  // tile A copied S(0) out
       mma_s(1, kslot);
-      umma_commit(&s_full[1]);
       umma_commit(&kv_empty[kslot]);
       for (int j = 0; j < n_kv; ++j) {
         const bool more = j + 1 < n_kv;
-        mbar_wait(&kv_full[slot], phase);  // V_j
-        const uint32_t vslot = slot;
-        advance();
-        // ---- tile A
+        if (more) {
+          kslot = take();   // K_{j+1}
+          wait_s_free();    // tile B copied S_B(j) out
+          mma_s(0, kslot);  // S_A(j+1): ready long before softmax A finishes tile j
+        }
+        const uint32_t vslot = take();  // V_j
         mbar_wait(&p_full[0], j & 1);
         tc_fence_after();
         mma_pv(0, vslot, j == 0);
         if (more) {
-          mbar_wait(&kv_full[slot], phase);  // K_{j+1}
-          tc_fence_after();
-          kslot = slot;
-          advance();
-          mma_s(0, kslot);
+          wait_s_free();  // tile A copied S_A(j+1) out
+          mma_s(1, kslot);
+          umma_commit(&kv_empty[kslot]);
         }
-        umma_commit(&s_full[0]);
-        // ---- tile B
         mbar_wait(&p_full[1], j & 1);
         tc_fence_after();
         mma_pv(1, vslot, j == 0);
         umma_commit(&kv_empty[vslot]);
-        if (more) {
-          mma_s(1, kslot);
-          umma_commit(&s_full[1]);
-          umma_commit(&kv_empty[kslot]);
-        } else {
-          umma_commit(&s_full[1]);
-        }
       }
     }
+    // no code is shared after the role split (ptxas sizes each setmaxnreg region separately only then)
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+      tc_fence_after();
+      tmem_dealloc(tmem_base, 512);
+    }
+    return;
   } else {
     // ===== softmax warpgroups (warps 0-3: tile A, warps 4-7: tile B) =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;\n");
     const int t = warp >> 2;
     const uint32_t lane_base = ((warp & 3u) * 32u) << 16;
-    const uint32_t tS = tmem_base + lane_base + t * 128;
+    const uint32_t tS = tmem_base + lane_base;
+    const uint32_t tP = tmem_base + lane_base + 128 + t * 64;
     const uint32_t tO = tmem_base + lane_base + 256 + t * 128;
     const float c = p.scale_log2;
     float m_used = 0.0f;  // reference max (raw score units) the stored exponentials are relative to
     float l = 0.0f;       // running row sum (relative to m_used)
-    uint32_t sphase = 0;
     for (int j = 0; j < n_kv; ++j) {
-      mbar_wait(&s_full[t], sphase);
-      sphase ^= 1;
+      mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
       uint32_t s[128];
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) tmem_ld32(tS + cc * 32, s + cc * 32);
       tc_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);  // the score buffer may be overwritten by the next QK
       // 8 independent max chains (a single dependent FMNMX chain costs ~6 clk per link: 400 clk per tile
       // in the round-1 profile)
       float mxs[8];
@@ -237,7 +268,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       } else {
         const bool grow = (mx - m_used) * c > 8.0f;
         if (__any_sync(0xffffffffu, grow)) {
-          // s_full(j) was committed after PV(j-1): O already holds every earlier contribution.
+          // O must hold every earlier contribution before it is rescaled: wait for PV(j-1)
+          mbar_wait(&pv_done[t], (j - 1) & 1);
+          tc_fence_after();
           const float m_new = fmaxf(m_used, mx);
           const float alpha = ex2_approx((m_used - m_new) * c);
           m_used = m_new;
@@ -269,15 +302,21 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           ls[(2 * i + 1) & 3] += b;
           pk[i] = pack_bf16x2(a, b);
         }
-        tmem_st32(tS + hh * 32, pk);
+        if (hh == 0 && j > 0) {
+          // P_t is still the A operand of PV(j-1) until that MMA has committed (normally long ago)
+          mbar_wait(&pv_done[t], (j - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st32(tP + hh * 32, pk);
       }
       l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&p_full[t]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
     }
     // final: PV(n_kv-1) complete
-    mbar_wait(&s_full[t], sphase);
+    mbar_wait(&pv_done[t], (n_kv - 1) & 1);
     tc_fence_after();
     const int row = q0 + t * ATT_TILE + (warp & 3) * 32 + lane;
     const float inv = 1.0f / l;
@@ -299,29 +338,26 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         }
       }
     }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
   }
 }
 
-namespace v2 {
-int attn_fwd_v2(const void* q, const void* k, const void* vt, void* o, int Lq, int Lk, int heads, int ldq,
+namespace v1 {
+int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, int Lk, int heads, int ldq,
                 int ldk, int ldo, int vt_chunk_len, float scale, cudaStream_t st);
 }
 
 int attn_fwd(const void* q, const void* k, const void* vt, void* o, int Lq, int Lk, int heads,
              int ldq, int ldk, int ldo, int vt_chunk_len, float scale, cudaStream_t st) {
-  static int use_v2 = -1;
-  if (use_v2 < 0) {
-    const char* e = getenv("G3C_ATTN_V2");
-    use_v2 = (e && atoi(e) != 0) ? 1 : 0;
+  // Default: the round-1 baseline kernel (attn_tcgen05_v1.cu), which measured 3-6 % faster on B200 than this
+  // decoupled-issue kernel (profiles/r01_attention_variants.txt).  G3C_ATTN_IMPL=v4 selects this one.
+  static int use_v1 = -1;
+  if (use_v1 < 0) {
+    const char* e = getenv("G3C_ATTN_IMPL");
+    use_v1 = (e && e[0] == 'v' && e[1] == '4') ? 0 : 1;
   }
-  if (use_v2) return v2::attn_fwd_v2(q, k, vt, o, Lq, Lk, heads, ldq, ldk, ldo, vt_chunk_len, scale, st);
+  if (use_v1) return v1::attn_fwd_v1(q, k, vt, o, Lq, Lk, heads, ldq, ldk, ldo, vt_chunk_len, scale, st);
   G3C_REQUIRE(q && k && vt && o, "attn: null operand");
   G3C_REQUIRE(Lq > 0 && Lk > 0 && heads > 0, "attn: bad sizes");
   G3C_REQUIRE(Lk % ATT_TILE == 0, "attn: Lk=%d must be a multiple of 128", Lk);

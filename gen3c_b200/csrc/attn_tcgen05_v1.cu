@@ -1,5 +1,5 @@
-// Path D — attention forward, variant 2 (experimental, selected with G3C_ATTN_V2=1): 64-key KV tiles with
-// DOUBLE-BUFFERED S per query tile.  See attn_tcgen05.cu for the default kernel and the shared description.
+// Path D — attention forward, round-1 baseline kernel (kept selectable with G3C_ATTN_IMPL=v1 for A/B timing):
+// per-tile S buffers with P aliasing S; strict A/B alternation.  See attn_tcgen05.cu for the default kernel.
 //   O = softmax(Q K^T * scale) V        (reference: cosmos_predict1/diffusion/module/attention.py
 //   :282-297 `cal_attn` -> transformer_engine DotProductAttention(sbhd, no_mask, dropout 0);
 //   self-attention Lq = Lk = 56 320, cross-attention Lk = 512)
@@ -14,35 +14,27 @@
 // One CTA = 256 query rows (two 128-row tiles A/B) of one head, 320 threads:
 //   warps 0-3  softmax of tile A   (thread = one query row; S row read from TMEM into registers)
 //   warps 4-7  softmax of tile B
-//   warp  8    TMA producer: Q once, then K_j / V_j (64 keys each) through an 8-slot ring of 16 KB tiles
+//   warp  8    TMA producer: Q once, then K_j / V_j through a 4-slot ring of 32 KB tiles
 //   warp  9    TMEM allocator + single-thread MMA issuer
-// TMEM (512 columns), per Q tile t: S[t][0] S[t][1] (2 x 64 columns, DOUBLE-BUFFERED) and O[t] (128).
-// P (bf16) overwrites the first 32 columns of its S buffer and feeds the P·V MMA straight from TMEM.
-// Round-1 profiling (profiles/r01_attn_ncu_summary.txt) showed the single-buffered version latency-bound on
-// the chain softmax(j) -> PV(j) -> QK(j+1) -> softmax(j+1) (tensor pipe 56 %, softmax warps idle 49 %).
-// With two S buffers QK(j+2) only depends on PV(j) (which frees the buffer), so S(j+1) is already in TMEM
-// when softmax(j) finishes: the softmax warpgroups run back to back and the MMA issue order per KV step is
-//   PV_A(j) ; QK_A(j+2) ; PV_B(j) ; QK_B(j+2).
-// Online softmax keeps a lazily updated reference max: O / row-sum are only rescaled when the row max grew
-// by more than 2^8 (the rescale first waits for PV(j-1), tracked by its own commit barrier).
-// A fraction of the exponentials runs on the FMA pipe (ex2_poly) because MUFU (16 ex2/clk/SM) is exactly as
-// slow as the two MMAs of a step.
+// TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,384) O_B [384,512); P (bf16) overwrites
+// the first 64 columns of its S tile and feeds the P·V MMA straight from TMEM.
+// MMA order per KV step j:  PV_A(j) ; S_A(j+1) ; PV_B(j) ; S_B(j+1)  — the S MMA of one tile and
+// the whole PV/S pair of the other overlap with that tile's softmax.
+// Online softmax keeps a lazily updated reference max: O / row-sum are only rescaled when the row
+// max grew by more than 2^8, so the TMEM read-modify-write of O is rare after the first tiles.
 #include <cstdlib>
 
 #include "kernels.h"
 
 namespace g3c {
-namespace v2 {
+namespace v1 {
 
 constexpr int ATT_THREADS = 320;
-constexpr int ATT_QTILE = 128;                   // rows per Q tile
-constexpr int ATT_KV = 64;                       // keys per KV tile
-constexpr int ATT_QTILE_BYTES = 128 * 128 * 2;   // 32 KB: two 64-column halves of 128 x 128 B
-constexpr int ATT_QHALF_BYTES = 128 * 128;       // 16 KB
-constexpr int ATT_SLOT_BYTES = 64 * 128 * 2;     // 16 KB: K tile (2 halves of 64 x 128 B) or V^T tile (128 x 128 B)
-constexpr int ATT_KHALF_BYTES = 64 * 128;        // 8 KB
-constexpr int ATT_SLOTS = 8;
-constexpr int ATT_SMEM = 2 * ATT_QTILE_BYTES + ATT_SLOTS * ATT_SLOT_BYTES + 512 + 1024;
+constexpr int ATT_TILE = 128;             // rows per Q tile, keys per KV tile, head dim
+constexpr int ATT_HALF_BYTES = 128 * 128; // one 64-column half of a 128x128 bf16 tile
+constexpr int ATT_TILE_BYTES = 2 * ATT_HALF_BYTES;
+constexpr int ATT_SLOTS = 4;
+constexpr int ATT_SMEM = 2 * ATT_TILE_BYTES + ATT_SLOTS * ATT_TILE_BYTES + 256 + 1024;
 
 struct AttnParams {
   int Lq, Lk, heads;
@@ -54,12 +46,13 @@ struct AttnParams {
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
   return y;
 }
 
-// 2^x on the FMA pipe: Cody-Waite split + degree-3 minimax polynomial (rel. err 7.5e-5, far below the bf16
-// rounding of P).
+// 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, rel. err 7.5e-5, far below the bf16
+// rounding of P): the MUFU unit delivers only 16 ex2/clk/SM, which is exactly as slow as the two MMAs of a
+// KV step; computing every kPolyEvery-th exponential here takes the softmax off the critical path.
 __device__ __forceinline__ float ex2_poly(float x) {
   x = fmaxf(x, -125.0f);
   const float xr = x + 12582912.0f;  // 1.5 * 2^23: low mantissa bits now hold round(x)
@@ -76,22 +69,21 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* smem_q = smem;                          // [2 tiles][2 halves][128 x 128 B]
-  uint8_t* smem_kv = smem + 2 * ATT_QTILE_BYTES;   // [slots][16 KB]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + ATT_SLOTS * ATT_SLOT_BYTES);
-  uint64_t* q_full = bars;                           // [1]
-  uint64_t* kv_full = bars + 1;                      // [slots]
-  uint64_t* kv_empty = bars + 1 + ATT_SLOTS;         // [slots]
-  uint64_t* s_full = bars + 1 + 2 * ATT_SLOTS;       // [tile][buf] -> 4
-  uint64_t* p_full = s_full + 4;                     // [tile][buf] -> 4
-  uint64_t* pv_done = p_full + 4;                    // [tile][buf] -> 4
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 4);
+  uint8_t* smem_q = smem;                        // [2 tiles][2 halves][128 x 128 B]
+  uint8_t* smem_kv = smem + 2 * ATT_TILE_BYTES;  // [slots][2 halves][128 x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + ATT_SLOTS * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;                        // [1]
+  uint64_t* kv_full = bars + 1;                   // [slots]
+  uint64_t* kv_empty = bars + 1 + ATT_SLOTS;      // [slots]
+  uint64_t* s_full = bars + 1 + 2 * ATT_SLOTS;    // [2]
+  uint64_t* p_full = bars + 3 + 2 * ATT_SLOTS;    // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5 + 2 * ATT_SLOTS);
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
   const int head = blockIdx.y;
-  const int q0 = blockIdx.x * 2 * ATT_QTILE;
-  const int n_kv = p.Lk / ATT_KV;
+  const int q0 = blockIdx.x * 2 * ATT_TILE;
+  const int n_kv = p.Lk / ATT_TILE;
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -102,10 +94,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 128);
-      mbar_init(&pv_done[i], 1);
     }
     fence_barrier_init();
   }
@@ -117,112 +108,102 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 
   if (warp == 8) {
     if (lane == 0) {
-      // ===== TMA producer =====  order: K0, K1, then per step j: V_j, K_{j+2}
-      mbar_expect_tx(q_full, 2 * ATT_QTILE_BYTES);
+      // ===== TMA producer =====
+      mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
 #pragma unroll
       for (int t = 0; t < 2; ++t)
 #pragma unroll
         for (int h = 0; h < 2; ++h)
-          tma_load_2d(smem_q + t * ATT_QTILE_BYTES + h * ATT_QHALF_BYTES, &tmQ, q_full, head * 128 + h * 64,
-                      q0 + t * ATT_QTILE);
+          tma_load_2d(smem_q + t * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmQ, q_full,
+                      head * 128 + h * 64, q0 + t * ATT_TILE);
       uint32_t slot = 0, phase = 0;
-      auto load_k = [&](int j) {
+      for (int j = 0; j < n_kv; ++j) {
+        const int kv0 = j * ATT_TILE;
+        // K_j
         mbar_wait(&kv_empty[slot], phase ^ 1);
-        mbar_expect_tx(&kv_full[slot], ATT_SLOT_BYTES);
+        mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
 #pragma unroll
         for (int h = 0; h < 2; ++h)
-          tma_load_2d(smem_kv + slot * ATT_SLOT_BYTES + h * ATT_KHALF_BYTES, &tmK, &kv_full[slot],
-                      head * 128 + h * 64, j * ATT_KV);
+          tma_load_2d(smem_kv + slot * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmK, &kv_full[slot],
+                      head * 128 + h * 64, kv0);
         if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; }
-      };
-      auto load_v = [&](int j) {
+        // V_j  (transposed: rows = head dim, columns = keys)
         mbar_wait(&kv_empty[slot], phase ^ 1);
-        mbar_expect_tx(&kv_full[slot], ATT_SLOT_BYTES);
-        const int kv0 = j * ATT_KV;
+        mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
         const int chunk = kv0 / p.vt_chunk_len;
-        tma_load_3d(smem_kv + slot * ATT_SLOT_BYTES, &tmV, &kv_full[slot], kv0 - chunk * p.vt_chunk_len,
-                    head * 128, chunk);
+        const int koff = kv0 - chunk * p.vt_chunk_len;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d(smem_kv + slot * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmV, &kv_full[slot],
+                      koff + h * 64, head * 128, chunk);
         if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; }
-      };
-      load_k(0);
-      if (n_kv > 1) load_k(1);
-      for (int j = 0; j < n_kv; ++j) {
-        load_v(j);
-        if (j + 2 < n_kv) load_k(j + 2);
       }
     }
   } else if (warp == 9) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      constexpr uint32_t idesc_qk = make_idesc_bf16(128, ATT_KV);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 128);
+      constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+      const uint32_t tS[2] = {tmem_base, tmem_base + 128};
+      const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
       uint32_t slot = 0, phase = 0;
-      auto take = [&]() {  // wait for the next ring slot to be filled, return its index
-        mbar_wait(&kv_full[slot], phase);
-        const uint32_t s = slot;
-        if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; }
-        return s;
-      };
-      auto mma_qk = [&](int t, int b, uint32_t kslot) {
-        // S[t][b] = Q_t K^T : 8 k-steps over the head dimension (two 64-wide halves)
-        const uint32_t d = tmem_base + t * 256 + b * 64;
+      auto advance = [&]() { if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; } };
+      auto mma_s = [&](int t, uint32_t kslot) {
+        // S_t = Q_t K^T : 8 k-steps over the head dimension
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t half = k >> 2, off = (k & 3) * 32;
-          const uint64_t da = make_sdesc_sw128(smem_u32(smem_q + t * ATT_QTILE_BYTES + half * ATT_QHALF_BYTES));
-          const uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + kslot * ATT_SLOT_BYTES + half * ATT_KHALF_BYTES));
-          umma_ss(d, sdesc_advance(da, off), sdesc_advance(db, off), idesc_qk, k != 0 ? 1u : 0u);
+          uint64_t da = make_sdesc_sw128(smem_u32(smem_q + t * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
+          uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + kslot * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
+          umma_ss(tS[t], sdesc_advance(da, off), sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
         }
-        umma_commit(&s_full[t * 2 + b]);
       };
-      auto mma_pv = [&](int t, int b, uint32_t vslot, bool first) {
-        // O[t] += P[t][b] V : 4 k-steps over the 64 keys; A = P from TMEM (bf16 pairs per column)
-        const uint32_t d = tmem_base + t * 256 + 128;
-        const uint32_t a = tmem_base + t * 256 + b * 64;
-        const uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + vslot * ATT_SLOT_BYTES));
+      auto mma_pv = [&](int t, uint32_t vslot, bool first) {
+        // O_t += P_t V : 8 k-steps over the 128 keys; A = P from TMEM (bf16 pairs per column)
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ts(d, a + k * 8, sdesc_advance(db, k * 32), idesc_pv, (first && k == 0) ? 0u : 1u);
-        umma_commit(&pv_done[t * 2 + b]);
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t half = k >> 2, off = (k & 3) * 32;
+          uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + vslot * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
+          umma_ts(tO[t], tS[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
+        }
       };
       mbar_wait(q_full, 0);
-      {
-        const uint32_t k0 = take();
-        tc_fence_after();
-        mma_qk(0, 0, k0);
-        mma_qk(1, 0, k0);
-        umma_commit(&kv_empty[k0]);
-        if (n_kv > 1) {
-          const uint32_t k1 = take();
-          tc_fence_after();
-          mma_qk(0, 1, k1);
-          mma_qk(1, 1, k1);
-          umma_commit(&kv_empty[k1]);
-        }
-      }
+      mbar_wait(&kv_full[slot], phase);
+      tc_fence_after();
+      uint32_t kslot = slot;
+      advance();
+      mma_s(0, kslot);
+      umma_commit(&s_full[0]);
+      mma_s(1, kslot);
+      umma_commit(&s_full[1]);
+      umma_commit(&kv_empty[kslot]);
       for (int j = 0; j < n_kv; ++j) {
-        const int b = j & 1;
-        const uint32_t par = (j >> 1) & 1;
-        const bool more = j + 2 < n_kv;
-        const uint32_t vslot = take();  // V_j
+        const bool more = j + 1 < n_kv;
+        mbar_wait(&kv_full[slot], phase);  // V_j
+        const uint32_t vslot = slot;
+        advance();
         // ---- tile A
-        mbar_wait(&p_full[0 * 2 + b], par);
+        mbar_wait(&p_full[0], j & 1);
         tc_fence_after();
-        mma_pv(0, b, vslot, j == 0);
-        uint32_t kslot = 0;
+        mma_pv(0, vslot, j == 0);
         if (more) {
-          kslot = take();  // K_{j+2}
+          mbar_wait(&kv_full[slot], phase);  // K_{j+1}
           tc_fence_after();
-          mma_qk(0, b, kslot);
+          kslot = slot;
+          advance();
+          mma_s(0, kslot);
         }
+        umma_commit(&s_full[0]);
         // ---- tile B
-        mbar_wait(&p_full[1 * 2 + b], par);
+        mbar_wait(&p_full[1], j & 1);
         tc_fence_after();
-        mma_pv(1, b, vslot, j == 0);
+        mma_pv(1, vslot, j == 0);
         umma_commit(&kv_empty[vslot]);
         if (more) {
-          mma_qk(1, b, kslot);
+          mma_s(1, kslot);
+          umma_commit(&s_full[1]);
           umma_commit(&kv_empty[kslot]);
+        } else {
+          umma_commit(&s_full[1]);
         }
       }
     }
@@ -230,25 +211,27 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     // ===== softmax warpgroups (warps 0-3: tile A, warps 4-7: tile B) =====
     const int t = warp >> 2;
     const uint32_t lane_base = ((warp & 3u) * 32u) << 16;
-    const uint32_t tS = tmem_base + lane_base + t * 256;
-    const uint32_t tO = tS + 128;
+    const uint32_t tS = tmem_base + lane_base + t * 128;
+    const uint32_t tO = tmem_base + lane_base + 256 + t * 128;
     const float c = p.scale_log2;
     float m_used = 0.0f;  // reference max (raw score units) the stored exponentials are relative to
     float l = 0.0f;       // running row sum (relative to m_used)
+    uint32_t sphase = 0;
     for (int j = 0; j < n_kv; ++j) {
-      const int b = j & 1;
-      mbar_wait(&s_full[t * 2 + b], (j >> 1) & 1);
+      mbar_wait(&s_full[t], sphase);
+      sphase ^= 1;
       tc_fence_after();
-      uint32_t s[64];
-      tmem_ld32(tS + b * 64, s);
-      tmem_ld32(tS + b * 64 + 32, s + 32);
+      uint32_t s[128];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) tmem_ld32(tS + cc * 32, s + cc * 32);
       tc_wait_ld();
-      // 8 independent max chains (a single dependent FMNMX chain costs ~6 clk per link)
+      // 8 independent max chains (a single dependent FMNMX chain costs ~6 clk per link: 400 clk per tile
+      // in the round-1 profile)
       float mxs[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) mxs[i] = __uint_as_float(s[i]);
 #pragma unroll
-      for (int i = 8; i < 64; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], __uint_as_float(s[i]));
+      for (int i = 8; i < 128; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], __uint_as_float(s[i]));
       const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
                              fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
       if (j == 0) {
@@ -256,9 +239,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       } else {
         const bool grow = (mx - m_used) * c > 8.0f;
         if (__any_sync(0xffffffffu, grow)) {
-          // O may still be accumulating PV(j-1): wait for its commit before the read-modify-write
-          mbar_wait(&pv_done[t * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
-          tc_fence_after();
+          // s_full(j) was committed after PV(j-1): O already holds every earlier contribution.
           const float m_new = fmaxf(m_used, mx);
           const float alpha = ex2_approx((m_used - m_new) * c);
           m_used = m_new;
@@ -276,29 +257,31 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         }
       }
       const float neg = -m_used * c;
-      uint32_t pk[32];
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float xa = fmaf(__uint_as_float(s[2 * i]), c, neg);
-        const float xb = fmaf(__uint_as_float(s[2 * i + 1]), c, neg);
-        const float a = ex2_approx(xa);
-        const float bb = (kPolyEvery > 0 && (i % (kPolyEvery / 2 > 0 ? kPolyEvery / 2 : 1)) == 0) ? ex2_poly(xb)
-                                                                                                    : ex2_approx(xb);
-        ls[(2 * i) & 3] += a;
-        ls[(2 * i + 1) & 3] += bb;
-        pk[i] = pack_bf16x2(a, bb);
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float xa = fmaf(__uint_as_float(s[hh * 64 + 2 * i]), c, neg);
+          const float xb = fmaf(__uint_as_float(s[hh * 64 + 2 * i + 1]), c, neg);
+          float a = ex2_approx(xa);
+          float b = (kPolyEvery > 0 && (i % (kPolyEvery / 2 > 0 ? kPolyEvery / 2 : 1)) == 0) ? ex2_poly(xb) : ex2_approx(xb);
+          ls[(2 * i) & 3] += a;
+          ls[(2 * i + 1) & 3] += b;
+          pk[i] = pack_bf16x2(a, b);
+        }
+        tmem_st32(tS + hh * 32, pk);
       }
       l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-      tmem_st32(tS + b * 64, pk);
       tc_wait_st();
       tc_fence_before();
-      mbar_arrive(&p_full[t * 2 + b]);
+      mbar_arrive(&p_full[t]);
     }
     // final: PV(n_kv-1) complete
-    mbar_wait(&pv_done[t * 2 + ((n_kv - 1) & 1)], ((n_kv - 1) >> 1) & 1);
+    mbar_wait(&s_full[t], sphase);
     tc_fence_after();
-    const int row = q0 + t * ATT_QTILE + (warp & 3) * 32 + lane;
+    const int row = q0 + t * ATT_TILE + (warp & 3) * 32 + lane;
     const float inv = 1.0f / l;
     __nv_bfloat16* optr = p.O + (size_t)row * p.ldo + head * 128;
 #pragma unroll 1
@@ -328,13 +311,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
   }
 }
 
-int attn_fwd_v2(const void* q, const void* k, const void* vt, void* o, int Lq, int Lk, int heads,
-             int ldq, int ldk, int ldo, int vt_chunk_len, float scale, cudaStream_t st) {
+int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, int Lk, int heads,
+                int ldq, int ldk, int ldo, int vt_chunk_len, float scale, cudaStream_t st) {
   G3C_REQUIRE(q && k && vt && o, "attn: null operand");
   G3C_REQUIRE(Lq > 0 && Lk > 0 && heads > 0, "attn: bad sizes");
-  G3C_REQUIRE(Lk % 128 == 0, "attn: Lk=%d must be a multiple of 128", Lk);
+  G3C_REQUIRE(Lk % ATT_TILE == 0, "attn: Lk=%d must be a multiple of 128", Lk);
   if (vt_chunk_len <= 0) vt_chunk_len = Lk;
-  G3C_REQUIRE(Lk % vt_chunk_len == 0 && vt_chunk_len % 128 == 0,
+  G3C_REQUIRE(Lk % vt_chunk_len == 0 && vt_chunk_len % ATT_TILE == 0,
               "attn: vt_chunk_len=%d must divide Lk=%d and be a multiple of 128", vt_chunk_len, Lk);
   G3C_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldo % 8 == 0 && ldq >= heads * 128 &&
                   ldk >= heads * 128 && ldo >= heads * 128,
@@ -349,7 +332,7 @@ int attn_fwd_v2(const void* q, const void* k, const void* vt, void* o, int Lq, i
   }
   {
     uint64_t dims[2] = {(uint64_t)heads * 128, (uint64_t)Lk}, str[1] = {(uint64_t)ldk * 2};
-    uint32_t box[2] = {64, ATT_KV};
+    uint32_t box[2] = {64, 128};
     int rc = make_tmap_bf16_sw128(&tmK, k, 2, dims, str, box);
     if (rc) return rc;
   }
@@ -357,7 +340,7 @@ int attn_fwd_v2(const void* q, const void* k, const void* vt, void* o, int Lq, i
     const int chunks = Lk / vt_chunk_len;
     uint64_t dims[3] = {(uint64_t)vt_chunk_len, (uint64_t)heads * 128, (uint64_t)chunks};
     uint64_t str[2] = {(uint64_t)vt_chunk_len * 2, (uint64_t)vt_chunk_len * 2 * heads * 128};
-    uint32_t box[3] = {ATT_KV, 128, 1};
+    uint32_t box[3] = {64, 128, 1};
     int rc = make_tmap_bf16_sw128(&tmV, vt, 3, dims, str, box);
     if (rc) return rc;
   }
@@ -380,7 +363,7 @@ int attn_fwd_v2(const void* q, const void* k, const void* vt, void* o, int Lq, i
   p.vt_chunk_len = vt_chunk_len;
   p.O = reinterpret_cast<__nv_bfloat16*>(o);
   p.scale_log2 = scale * 1.4426950408889634f;
-  dim3 grid((Lq + 2 * ATT_QTILE - 1) / (2 * ATT_QTILE), heads);
+  dim3 grid((Lq + 2 * ATT_TILE - 1) / (2 * ATT_TILE), heads);
   switch (poly) {
     case 0: k_attn_fwd<0><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
     case 2: k_attn_fwd<2><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
@@ -391,5 +374,5 @@ int attn_fwd_v2(const void* q, const void* k, const void* vt, void* o, int Lq, i
   return G3C_OK;
 }
 
-}  // namespace v2
+}  // namespace v1
 }  // namespace g3c

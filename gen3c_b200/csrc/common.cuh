@@ -100,11 +100,18 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
   return t;
 }
-static __device__ __noinline__ void mbar_timeout_trap(uint32_t bar, uint32_t parity) {
-  printf("g3c: mbarrier timeout block(%d,%d) thread %d bar@%u parity %u\n", blockIdx.x,
-         blockIdx.y, threadIdx.x, bar, parity);
-  __trap();
-}
+// A protocol bug must trap instead of hanging the GPU box.  No function call / printf here: a call inside a
+// setmaxnreg region forces ptxas to size the whole kernel for the smallest register budget.
+#ifdef G3C_MBAR_DEBUG
+#define G3C_MBAR_TIMEOUT_ACTION(bar, parity)                                                                 \
+  do {                                                                                                       \
+    printf("g3c: mbarrier timeout block(%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y,        \
+           threadIdx.x, bar, parity);                                                                        \
+    __trap();                                                                                                \
+  } while (0)
+#else
+#define G3C_MBAR_TIMEOUT_ACTION(bar, parity) asm volatile("trap;\n")
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
@@ -113,7 +120,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if ((++spins & 0xFFFu) == 0) {
       uint64_t now = global_timer_ns();
       if (t0 == 0) t0 = now;
-      else if (now - t0 > G3C_MBAR_TIMEOUT_NS) mbar_timeout_trap(smem_u32(bar), parity);
+      else if (now - t0 > G3C_MBAR_TIMEOUT_NS) G3C_MBAR_TIMEOUT_ACTION(smem_u32(bar), parity);
     }
   }
 }
