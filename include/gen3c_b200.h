@@ -105,6 +105,11 @@ int g3c_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, in
 int g3c_attn_fwd(const void* q, const void* k, const void* vt, void* o, int Lq, int Lk, int heads,
                  int ldq, int ldk, int ldo, int vt_chunk_len, float scale, void* stream);
 
+/* Profiling aid: when a device buffer of 3*64*8 uint64 is registered, the next g3c_attn_fwd launches run a
+ * traced build of the kernel in which CTA (0,0) records clock64() stamps per KV step: role 0 = MMA issuer,
+ * 1/2 = softmax tile A/B.  NULL switches tracing off.  (tools/attn_trace.py prints the timeline.) */
+int g3c_attn_set_trace(unsigned long long* device_buffer);
+
 /* x (f32 [L,D]) += pos (bf16, optional) ; y (bf16) = LayerNorm_eps(x) * (1 + scale) + shift
  * reference: module/blocks.py:339-341, :547-548 */
 int g3c_ln_modulate(float* x, const void* pos_bf16, const float* shift, const float* scale,

@@ -118,3 +118,43 @@ def test_product_path_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("# oracle-free", ""), f"{f} mentions the oracle"
+
+
+def test_condition_assembly_host_logic():
+    """D12: add_condition_video_indicator_and_video_input_mask / encode_warped_frames / add_condition_pose against the
+    reference semantics (model_v2w.py:32-82, model_gen3c.py:32-57,115-139) with a synthetic encoder."""
+    from gen3c_b200 import model_gen3c as mg
+
+    B, T, H, W = 1, 4, 8, 8
+    lat = torch.randn(B, 16, T, H, W)
+    c = mg.VideoExtendCondition(crossattn_emb=torch.zeros(1, 4, 8), video_cond_bool=True)
+    c = mg.add_condition_video_indicator_and_video_input_mask(lat, c, num_condition_t=1)
+    assert c.condition_video_indicator.shape == (1, 1, T, 1, 1) and float(c.condition_video_indicator.sum()) == 1.0
+    assert c.condition_video_input_mask.shape == (B, 1, T, H, W)
+    assert float(c.condition_video_input_mask[:, :, 0].min()) == 1.0 and float(c.condition_video_input_mask[:, :, 1:].max()) == 0.0
+    u = mg.VideoExtendCondition(crossattn_emb=torch.zeros(1, 4, 8), video_cond_bool=False)
+    u = mg.add_condition_video_indicator_and_video_input_mask(lat, u, 1)
+    assert float(u.condition_video_input_mask.abs().max()) == 0.0
+    with pytest.raises(AssertionError):
+        mg.add_condition_video_indicator_and_video_input_mask(lat, c, None)
+
+    F = 9
+    enc_calls = []
+
+    def encode(x):  # [B,3,F,h,w] -> [B,16,T,H,W]
+        enc_calls.append(float(x.float().mean()))
+        return torch.full((B, 16, T, H, W), float(x.float().mean()))
+
+    state = torch.rand(B, F, 1, 3, 16, 16)           # one buffer, frame_buffer_max = 2 -> zero padded
+    mask = torch.ones(B, F, 1, 1, 16, 16)
+    lc = mg.encode_warped_frames(state, mask, encode, frame_buffer_max=2, dtype=torch.float32)
+    assert lc.shape == (B, 64, T, H, W)
+    assert abs(enc_calls[1] - 1.0) < 1e-6            # mask * 2 - 1 = 1, repeated to 3 channels
+    assert float(lc[:, 32:].abs().max()) == 0.0      # second buffer slot is zero
+    c = mg.add_condition_pose(lc, c)
+    u = mg.add_condition_pose(lc, u, drop_out_latent=True)
+    assert torch.equal(c.condition_video_pose, lc) and float(u.condition_video_pose.abs().max()) == 0.0
+    cond, uncond = mg.get_conditions(torch.zeros(1, 4, 8), torch.ones(1, 4, 8), torch.zeros(1, 1, 16, 16), state, mask, lat,
+                                     1, encode, dtype=torch.float32)
+    assert torch.equal(cond.condition_video_input_mask, uncond.condition_video_input_mask)  # add_input_frames_guidance=False
+    assert set(cond.to_dict()) >= {"crossattn_emb", "condition_video_pose", "condition_video_input_mask", "gt_latent"}

@@ -109,3 +109,40 @@ def test_engine_errors_are_loud():
     inp = cases.dit_inputs(cfg, 1, 6, 6, 128)  # 1*3*3 = 9 tokens: not a multiple of 128
     with pytest.raises(_lib.G3CError):
         run_net(net, inp, inp["pose"], inp["ctx_c"], 1)
+
+
+def test_sampler_loop_matches_oracle_loop():
+    """Three steps of generate_samples_from_batch (D1) on the tiny net against the oracle loop: conditions assembled by
+    the host mirrors (D12), loop body = g3c_denoise_step."""
+    from gen3c_b200 import model_gen3c as mg
+
+    cfg, shp = cases.TINY, cases.TINY_SHAPE
+    T, H, W, M = shp["T"], shp["H"], shp["W"], shp["ctx_len"]
+    sd = dit_oracle.random_state_dict(cfg, seed=0)
+    net = build_net(cfg, sd)
+    inp = cases.dit_inputs(cfg, **shp)
+    bf = torch.bfloat16
+    steps, guidance = 3, 1.0
+    xt0 = (torch.randn(1, 16, T, H, W, generator=torch.Generator().manual_seed(9)) * 80.0).to(bf)
+    cond = mg.VideoExtendCondition(crossattn_emb=inp["ctx_c"][None].cuda(), padding_mask=torch.zeros(1, 1, H * 8, W * 8).cuda(),
+                                   fps=torch.tensor([24.0]), video_cond_bool=True)
+    unc = mg.VideoExtendCondition(crossattn_emb=inp["ctx_u"][None].cuda(), padding_mask=cond.padding_mask,
+                                  fps=cond.fps, video_cond_bool=True)
+    lat = inp["gt"][None].cuda().to(bf)
+    cond = mg.add_condition_pose(inp["pose"][None].cuda().to(bf), mg.add_condition_video_indicator_and_video_input_mask(lat, cond, 1))
+    unc = mg.add_condition_pose(inp["pose"][None].cuda().to(bf), mg.add_condition_video_indicator_and_video_input_mask(lat, unc, 1), True)
+    got = mg.generate_samples_from_batch(net, cond, unc, guidance=guidance, seed=1, state_shape=(16, T, H, W),
+                                         num_steps=steps, xt0=xt0)[0].float().cpu()
+    sig = dit_oracle.karras_sigmas(steps)
+    noise = torch.from_numpy(dit_oracle.arch_invariant_rand((1, 16, T, H, W), 1))[0]
+    ind = torch.zeros(T)
+    ind[0] = 1.0
+
+    def onet(x_in, t, c):
+        return dit_oracle.forward(sd, cfg, x_in, inp["cond_mask"], inp["pose"] if c else None, inp["padding"], t,
+                                  inp["ctx_c"] if c else inp["ctx_u"])
+
+    x = xt0[0].float()
+    for i in range(steps):
+        x = dit_oracle.denoise_step(onet, x, inp["gt"], noise, ind, float(sig[i]), float(sig[i + 1]), guidance)
+    assert rel(got, x) < 1e-2, rel(got, x)
