@@ -46,7 +46,15 @@ struct AttnParams {
   int vt_chunk_len;
   __nv_bfloat16* O;
   float scale_log2;  // softmax scale * log2(e)
+  unsigned long long* trace;  // kTrace only: [3 roles][64 steps][8 slots] clock64 stamps of CTA (0,0)
 };
+
+#define ATT_TR(role, slot)                                                                       \
+  do {                                                                                           \
+    if constexpr (kTrace) {                                                                      \
+      if (blockIdx.x == 0 && blockIdx.y == 0 && j < 64) p.trace[((role) * 64 + j) * 8 + (slot)] = clock64(); \
+    }                                                                                            \
+  } while (0)
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -66,7 +74,7 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
 }
 
-template <int kPolyEvery>
+template <int kPolyEvery, bool kTrace>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
     k_attn_fwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -205,21 +213,29 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       umma_commit(&kv_empty[kslot]);
       for (int j = 0; j < n_kv; ++j) {
         const bool more = j + 1 < n_kv;
+        ATT_TR(0, 0);
         if (more) {
           kslot = take();   // K_{j+1}
           wait_s_free();    // tile B copied S_B(j) out
+          ATT_TR(0, 1);
           mma_s(0, kslot);  // S_A(j+1): ready long before softmax A finishes tile j
+          ATT_TR(0, 2);
         }
         const uint32_t vslot = take();  // V_j
         mbar_wait(&p_full[0], j & 1);
+        ATT_TR(0, 3);
         tc_fence_after();
         mma_pv(0, vslot, j == 0);
+        ATT_TR(0, 4);
         if (more) {
           wait_s_free();  // tile A copied S_A(j+1) out
+          ATT_TR(0, 5);
           mma_s(1, kslot);
           umma_commit(&kv_empty[kslot]);
+          ATT_TR(0, 6);
         }
         mbar_wait(&p_full[1], j & 1);
+        ATT_TR(0, 7);
         tc_fence_after();
         mma_pv(1, vslot, j == 0);
         umma_commit(&kv_empty[vslot]);
@@ -244,13 +260,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     const float c = p.scale_log2;
     float m_used = 0.0f;  // reference max (raw score units) the stored exponentials are relative to
     float l = 0.0f;       // running row sum (relative to m_used)
+    const bool tr = kTrace && (warp & 3) == 0 && lane == 0;
     for (int j = 0; j < n_kv; ++j) {
+      if (tr) ATT_TR(1 + t, 0);
       mbar_wait(&s_full[t], j & 1);
+      if (tr) ATT_TR(1 + t, 1);
       tc_fence_after();
       uint32_t s[128];
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) tmem_ld32(tS + cc * 32, s + cc * 32);
       tc_wait_ld();
+      if (tr) ATT_TR(1 + t, 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_free);  // the score buffer may be overwritten by the next QK
@@ -288,6 +308,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         }
       }
       const float neg = -m_used * c;
+      if (tr) ATT_TR(1 + t, 3);
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
@@ -308,12 +329,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           tc_fence_after();
         }
         tmem_st32(tP + hh * 32, pk);
+        if (tr && hh == 0) ATT_TR(1 + t, 4);
       }
       l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       tc_wait_st();
+      if (tr) ATT_TR(1 + t, 5);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[t]);
+      if (tr) ATT_TR(1 + t, 6);
     }
     // final: PV(n_kv-1) complete
     mbar_wait(&pv_done[t], (n_kv - 1) & 1);
@@ -344,6 +368,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 }
 
 namespace v1 {
+extern unsigned long long* g_attn_trace;
 int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, int Lk, int heads, int ldq,
                 int ldk, int ldo, int vt_chunk_len, float scale, cudaStream_t st);
 }
@@ -393,12 +418,13 @@ int attn_fwd(const void* q, const void* k, const void* vt, void* o, int Lq, int 
   static int poly = -1;
   if (poly < 0) {
     const char* e = getenv("G3C_ATTN_POLY");
-    poly = e ? atoi(e) : 4;
+    poly = e ? atoi(e) : 0;
     if (poly != 0 && poly != 2 && poly != 4 && poly != 8) poly = 4;
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
   }
   AttnParams p;
   p.Lq = Lq;
@@ -409,11 +435,16 @@ int attn_fwd(const void* q, const void* k, const void* vt, void* o, int Lq, int 
   p.O = reinterpret_cast<__nv_bfloat16*>(o);
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((Lq + 2 * ATT_TILE - 1) / (2 * ATT_TILE), heads);
-  switch (poly) {
-    case 0: k_attn_fwd<0><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-    case 2: k_attn_fwd<2><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-    case 8: k_attn_fwd<8><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-    default: k_attn_fwd<4><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+  p.trace = v1::g_attn_trace;
+  if (p.trace) {
+    k_attn_fwd<0, true><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+  } else {
+    switch (poly) {
+      case 0: k_attn_fwd<0, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+      case 2: k_attn_fwd<2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+      case 8: k_attn_fwd<8, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+      default: k_attn_fwd<4, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
+    }
   }
   G3C_CUDA(cudaGetLastError());
   return G3C_OK;

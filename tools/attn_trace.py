@@ -1,4 +1,4 @@
-"""Per-phase clock64 timeline of one attention CTA (profiling aid).  Usage: python tools/attn_trace.py"""
+"""Per-phase clock64 timeline of one attention CTA (profiling aid; honours G3C_ATTN_IMPL=v1|v5)."""
 import sys
 
 import torch
