@@ -174,7 +174,7 @@ def run_ours(args):
     net = build_net(torch, dev)
     if world > 1:
         assert LAT[1] % world == 0, "16 latent frames must divide over the ranks"
-        net.enable_context_parallel(dist.group.WORLD)
+        net.enable_context_parallel(dist.group.WORLD, mode=args.cp_mode)
     Tl = LAT[1] // world
     t0 = rank * Tl
     bf = torch.bfloat16
@@ -274,7 +274,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "Cosmos-7B GEN3C DiT denoise step (cond + uncond forward + EDM Euler glue), latent "
                                "[16,16,88,160] = 56 320 tokens, ctx 512x1024, guidance 1, random-init weights",
-                   "parallelism": f"cp{world}", "l2": "inputs larger than L2 (14.5 GB weights, 0.9 GB residual stream)"},
+                   "parallelism": f"cp{world}" + (f" ({args.cp_mode or os.environ.get('G3C_CP_MODE', 'p2p')} K/V exchange)" if world > 1 else ""), "l2": "inputs larger than L2 (14.5 GB weights, 0.9 GB residual stream)"},
         "e2e": {"value": 1e3 / ms_e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "tensor", "kernel": "k_attn_fwd (self-attention)", "achieved": achieved, "peak": peak,
@@ -304,6 +304,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cp-mode", default=None, choices=[None, "p2p", "nccl"],
+                    help="context-parallel K/V exchange: p2p = fused projection -> peer-memory all-gather (default), nccl = ncclAllGather")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

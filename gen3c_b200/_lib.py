@@ -86,6 +86,9 @@ SIGNATURES = {
     "g3c_dit_load": (_I, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), _I, _I]),
     "g3c_nccl_unique_id": (_I, [_P]),
     "g3c_dit_enable_cp": (_I, [_P, _P, _I, _I]),
+    "g3c_dit_cp_export": (_I, [_P, _P]),
+    "g3c_dit_cp_import": (_I, [_P, _P, _I]),
+    "g3c_dit_cp_mode": (_I, [_P]),
     "g3c_dit_disable_cp": (_I, [_P]),
     "g3c_dit_set_shape": (_I, [_P, _I, _I, _I, _I, _F]),
     "g3c_dit_forward": (_I, [_P, _P, _P, _P, _P, _F, _P, _P, _P]),

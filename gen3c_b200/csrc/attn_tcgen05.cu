@@ -370,11 +370,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 namespace v1 {
 extern unsigned long long* g_attn_trace;
 int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, int Lk, int heads, int ldq,
-                int ldk, int ldo, int vt_chunk_len, float scale, cudaStream_t st);
+                int ldk, int ldo, int vt_chunk_len, float scale, cudaStream_t st, const ChunkGate* gate);
 }
 
 int attn_fwd(const void* q, const void* k, const void* vt, void* o, int Lq, int Lk, int heads,
-             int ldq, int ldk, int ldo, int vt_chunk_len, float scale, cudaStream_t st) {
+             int ldq, int ldk, int ldo, int vt_chunk_len, float scale, cudaStream_t st, const ChunkGate* gate) {
   // Default: the round-1 baseline kernel (attn_tcgen05_v1.cu), which measured 3-6 % faster on B200 than this
   // decoupled-issue kernel (profiles/r01_attention_variants.txt).  G3C_ATTN_IMPL=v4 selects this one.
   static int use_v1 = -1;
@@ -382,7 +382,7 @@ int attn_fwd(const void* q, const void* k, const void* vt, void* o, int Lq, int 
     const char* e = getenv("G3C_ATTN_IMPL");
     use_v1 = (e && e[0] == 'v' && e[1] == '4') ? 0 : 1;
   }
-  if (use_v1) return v1::attn_fwd_v1(q, k, vt, o, Lq, Lk, heads, ldq, ldk, ldo, vt_chunk_len, scale, st);
+  if (use_v1 || gate) return v1::attn_fwd_v1(q, k, vt, o, Lq, Lk, heads, ldq, ldk, ldo, vt_chunk_len, scale, st, gate);
   G3C_REQUIRE(q && k && vt && o, "attn: null operand");
   G3C_REQUIRE(Lq > 0 && Lk > 0 && heads > 0, "attn: bad sizes");
   G3C_REQUIRE(Lk % ATT_TILE == 0, "attn: Lk=%d must be a multiple of 128", Lk);
@@ -456,5 +456,5 @@ extern "C" int g3c_attn_fwd(const void* q, const void* k, const void* vt, void* 
                             int heads, int ldq, int ldk, int ldo, int vt_chunk_len, float scale,
                             void* stream) {
   return g3c::attn_fwd(q, k, vt, o, Lq, Lk, heads, ldq, ldk, ldo, vt_chunk_len, scale,
-                       (cudaStream_t)stream);
+                       (cudaStream_t)stream, nullptr);
 }

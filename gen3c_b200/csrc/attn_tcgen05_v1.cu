@@ -42,6 +42,9 @@ struct AttnParams {
   int vt_chunk_len;
   __nv_bfloat16* O;
   float scale_log2;  // softmax scale * log2(e)
+  const uint32_t* chunk_flags;  // context-parallel gate (or NULL): chunk c readable once chunk_flags[c] >= flag_seq
+  uint32_t flag_seq;
+  int first_chunk;
   unsigned long long* trace;  // kTrace only: [3 roles][64 steps][8 slots] clock64 stamps of CTA (0,0)
 };
 
@@ -125,8 +128,29 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           tma_load_2d(smem_q + t * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmQ, q_full,
                       head * 128 + h * 64, q0 + t * ATT_TILE);
       uint32_t slot = 0, phase = 0;
+      const int tiles_per_chunk = p.vt_chunk_len / ATT_TILE;
+      const int n_chunks = p.Lk / p.vt_chunk_len;
       for (int j = 0; j < n_kv; ++j) {
-        const int kv0 = j * ATT_TILE;
+        // KV tiles are visited chunk by chunk starting with `first_chunk` (the local one under context
+        // parallelism); a remote chunk is only touched after its producer rank has published it.
+        int chunk = p.first_chunk + j / tiles_per_chunk;
+        if (chunk >= n_chunks) chunk -= n_chunks;
+        const int within = j % tiles_per_chunk;
+        if (p.chunk_flags && within == 0) {
+          uint32_t v, spins = 0;
+          uint64_t t0 = 0;
+          for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p.chunk_flags + chunk) : "memory");
+            if ((int)(v - p.flag_seq) >= 0) break;
+            if ((++spins & 0x3FFu) == 0) {
+              const uint64_t now = global_timer_ns();
+              if (t0 == 0) t0 = now;
+              else if (now - t0 > G3C_MBAR_TIMEOUT_NS) asm volatile("trap;\n");
+            }
+          }
+          asm volatile("fence.proxy.async.global;\n" ::: "memory");  // peer-written data is read by the TMA next
+        }
+        const int kv0 = chunk * p.vt_chunk_len + within * ATT_TILE;
         // K_j
         mbar_wait(&kv_empty[slot], phase ^ 1);
         mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
@@ -138,8 +162,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         // V_j  (transposed: rows = head dim, columns = keys)
         mbar_wait(&kv_empty[slot], phase ^ 1);
         mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
-        const int chunk = kv0 / p.vt_chunk_len;
-        const int koff = kv0 - chunk * p.vt_chunk_len;
+        const int koff = within * ATT_TILE;
 #pragma unroll
         for (int h = 0; h < 2; ++h)
           tma_load_3d(smem_kv + slot * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmV, &kv_full[slot],
@@ -335,7 +358,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 unsigned long long* g_attn_trace = nullptr;  // set through g3c_attn_set_trace (profiling aid, not a product path)
 
 int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, int Lk, int heads,
-                int ldq, int ldk, int ldo, int vt_chunk_len, float scale, cudaStream_t st) {
+                int ldq, int ldk, int ldo, int vt_chunk_len, float scale, cudaStream_t st, const ChunkGate* gate) {
   G3C_REQUIRE(q && k && vt && o, "attn: null operand");
   G3C_REQUIRE(Lq > 0 && Lk > 0 && heads > 0, "attn: bad sizes");
   G3C_REQUIRE(Lk % ATT_TILE == 0, "attn: Lk=%d must be a multiple of 128", Lk);
@@ -388,6 +411,10 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
   p.O = reinterpret_cast<__nv_bfloat16*>(o);
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((Lq + 2 * ATT_TILE - 1) / (2 * ATT_TILE), heads);
+  p.chunk_flags = gate ? gate->flags : nullptr;
+  p.flag_seq = gate ? gate->seq : 0;
+  p.first_chunk = gate ? gate->first : 0;
+  G3C_REQUIRE(p.first_chunk >= 0 && p.first_chunk < Lk / vt_chunk_len, "attn: first chunk %d out of range", p.first_chunk);
   p.trace = g_attn_trace;
   if (g_attn_trace) {
     k_attn_fwd<0, true><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);

@@ -107,9 +107,17 @@ struct g3c_dit {
   float fps = 24.f;
   // cp
   int cp_rank = 0, cp_size = 1;
-  ncclComm_t comm = nullptr;
+  ncclComm_t comm = nullptr;  // only in the NCCL all-gather mode (G3C_CP_MODE=nccl)
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t ev_kv = nullptr, ev_gathered = nullptr;
+  // default CP mode: fused projection -> all-gather through NVLink peer memory.  One cudaMalloc'd region per
+  // rank, IPC-mapped by every peer: K / V^T of all ranks, double buffered by layer parity, plus arrival flags.
+  bool cp_p2p = true;
+  void* cp_region = nullptr;
+  size_t cp_region_bytes = 0, off_k[2] = {0, 0}, off_vt[2] = {0, 0}, off_flags = 0;
+  void* peer_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool peers_open = false;
+  uint32_t kv_seq = 0;
   // workspace
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -241,6 +249,16 @@ static int resolve(g3c_dit* h, cudaStream_t st) {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Publish "my K / V^T slices of layer `seq` have landed" in every rank's flag array.  Launched after the producer
+// kernels on the same stream (their peer writes are complete at kernel completion); release at system scope.
+__global__ void k_cp_signal(PeerDst slots, uint32_t seq) {
+  const int r = threadIdx.x;
+  if (r < slots.n) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(slots.ptr[r]), "r"(seq) : "memory");
+  }
+}
+
 static int build_tables(g3c_dit* h, cudaStream_t st) {
   if (h->tables_ready) return G3C_OK;
   const g3c_dit_config& c = h->cfg;
@@ -311,24 +329,60 @@ static int forward(g3c_dit* h, const void* x_in, const void* cond_mask, const vo
       const SubBlock& s = h->blk[i][0];
       const float* m = h->mods + (size_t)(i * 3 + 0) * 3 * D;
       K(CAT_ELTWISE, ln_modulate(h->x, h->pos, m, m + D, h->xn, L, D, 1e-6f, st));   // + abs-pos add
-      K(CAT_GEMM, gemm_bf16(h->xn, s.wk, k_loc, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
-      K(CAT_ELTWISE, rmsnorm_rope(k_loc, D, L, heads, s.gk, h->rope, 1e-6f, st));
-      K(CAT_GEMM, gemm_bf16(s.wv, h->xn, vt_loc, D, L, D, D, D, L, G3C_EPI_BF16, nullptr, 0, st));  // V^T
-      if (h->cp_size > 1) {
-        // one in-place all-gather of K and of V^T per layer, overlapped with the Q projection
-        G3C_CUDA(cudaEventRecord(h->ev_kv, st));
-        G3C_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_kv, 0));
-        G3C_NCCL(nccl().GroupStart());
-        G3C_NCCL(nccl().AllGather(k_loc, h->k_all, (size_t)L * D, kNcclBfloat16, h->comm, h->comm_stream));
-        G3C_NCCL(nccl().AllGather(vt_loc, h->vt_all, (size_t)L * D, kNcclBfloat16, h->comm, h->comm_stream));
-        G3C_NCCL(nccl().GroupEnd());
-        G3C_CUDA(cudaEventRecord(h->ev_gathered, h->comm_stream));
-        n += 2;
+      if (h->cp_size > 1 && h->cp_p2p) {
+        // fused projection -> all-gather: every rank stores its K / V^T slice straight into every peer's buffer
+        // (GEMM epilogue / RMSNorm-RoPE pass, NVLink posted writes), then raises a flag; attention starts on the
+        // local chunk at once and picks up the remote chunks as their flags arrive.
+        G3C_REQUIRE(h->peers_open, "dit_forward: context-parallel peers not imported (g3c_dit_cp_import)");
+        const uint32_t seq = ++h->kv_seq;
+        const int set = seq & 1, me = h->cp_rank;
+        const size_t slice = (size_t)L * D * 2;
+        char* reg = (char*)h->cp_region;
+        __nv_bfloat16* kb = (__nv_bfloat16*)(reg + h->off_k[set]);
+        __nv_bfloat16* vb = (__nv_bfloat16*)(reg + h->off_vt[set]);
+        __nv_bfloat16* kl = kb + (size_t)me * L * D;
+        __nv_bfloat16* vl = vb + (size_t)me * L * D;
+        PeerDst pk, pv, pf;
+        for (int r = 0; r < h->cp_size; ++r) {
+          char* pb = (char*)h->peer_base[r];
+          pf.ptr[pf.n++] = pb + h->off_flags + (size_t)(set * 8 + me) * 4;
+          if (r == me) continue;
+          pk.ptr[pk.n++] = pb + h->off_k[set] + (size_t)me * slice;
+          pv.ptr[pv.n++] = pb + h->off_vt[set] + (size_t)me * slice;
+        }
+        K(CAT_GEMM, gemm_bf16(h->xn, s.wk, kl, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
+        K(CAT_COMM, rmsnorm_rope(kl, D, L, heads, s.gk, h->rope, 1e-6f, st, &pk));
+        K(CAT_COMM, gemm_bf16(s.wv, h->xn, vl, D, L, D, D, D, L, G3C_EPI_BF16, nullptr, 0, st, &pv));  // V^T
+        k_cp_signal<<<1, 32, 0, st>>>(pf, seq);
+        G3C_CUDA(cudaGetLastError());
+        ++n;
+        K(CAT_GEMM, gemm_bf16(h->xn, s.wq, h->q, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
+        K(CAT_ELTWISE, rmsnorm_rope(h->q, D, L, heads, s.gq, h->rope, 1e-6f, st));
+        ChunkGate gate;
+        gate.flags = (const uint32_t*)(reg + h->off_flags) + set * 8;
+        gate.seq = seq;
+        gate.first = me;
+        K(CAT_ATTN_SELF, attn_fwd(h->q, kb, vb, h->att, L, Lk_all, heads, D, D, D, L, attn_scale, st, &gate));
+      } else {
+        K(CAT_GEMM, gemm_bf16(h->xn, s.wk, k_loc, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
+        K(CAT_ELTWISE, rmsnorm_rope(k_loc, D, L, heads, s.gk, h->rope, 1e-6f, st));
+        K(CAT_GEMM, gemm_bf16(s.wv, h->xn, vt_loc, D, L, D, D, D, L, G3C_EPI_BF16, nullptr, 0, st));  // V^T
+        if (h->cp_size > 1) {
+          // baseline mode (G3C_CP_MODE=nccl): one in-place all-gather of K and of V^T per layer on a side stream
+          G3C_CUDA(cudaEventRecord(h->ev_kv, st));
+          G3C_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_kv, 0));
+          G3C_NCCL(nccl().GroupStart());
+          G3C_NCCL(nccl().AllGather(k_loc, h->k_all, (size_t)L * D, kNcclBfloat16, h->comm, h->comm_stream));
+          G3C_NCCL(nccl().AllGather(vt_loc, h->vt_all, (size_t)L * D, kNcclBfloat16, h->comm, h->comm_stream));
+          G3C_NCCL(nccl().GroupEnd());
+          G3C_CUDA(cudaEventRecord(h->ev_gathered, h->comm_stream));
+          n += 2;
+        }
+        K(CAT_GEMM, gemm_bf16(h->xn, s.wq, h->q, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
+        K(CAT_ELTWISE, rmsnorm_rope(h->q, D, L, heads, s.gq, h->rope, 1e-6f, st));
+        if (h->cp_size > 1) G3C_CUDA(cudaStreamWaitEvent(st, h->ev_gathered, 0));
+        K(CAT_ATTN_SELF, attn_fwd(h->q, h->k_all, h->vt_all, h->att, L, Lk_all, heads, D, D, D, L, attn_scale, st));
       }
-      K(CAT_GEMM, gemm_bf16(h->xn, s.wq, h->q, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
-      K(CAT_ELTWISE, rmsnorm_rope(h->q, D, L, heads, s.gq, h->rope, 1e-6f, st));
-      if (h->cp_size > 1) G3C_CUDA(cudaStreamWaitEvent(st, h->ev_gathered, 0));
-      K(CAT_ATTN_SELF, attn_fwd(h->q, h->k_all, h->vt_all, h->att, L, Lk_all, heads, D, D, D, L, attn_scale, st));
       K(CAT_GEMM, gemm_bf16(h->att, s.wo, h->x, L, D, D, D, D, D, G3C_EPI_GATED_RESIDUAL_F32, m + 2 * D, 0, st));
     }
     // ---------------- CA: cross-attention to the T5 context (blocks.py:464-471)
@@ -381,7 +435,19 @@ int g3c_dit_create(const g3c_dit_config* cfg, g3c_dit_t** out) {
   return G3C_OK;
 }
 
+static void free_cp_region(g3c_dit* h) {
+  for (int r = 0; r < 8; ++r) {
+    if (h->peer_base[r] && h->peer_base[r] != h->cp_region) cudaIpcCloseMemHandle(h->peer_base[r]);
+    h->peer_base[r] = nullptr;
+  }
+  h->peers_open = false;
+  if (h->cp_region) cudaFree(h->cp_region);
+  h->cp_region = nullptr;
+  h->cp_region_bytes = 0;
+}
+
 static void free_ws(g3c_dit* h) {
+  free_cp_region(h);
   if (h->ws) cudaFree(h->ws);
   h->ws = nullptr;
   h->ws_bytes = 0;
@@ -428,18 +494,21 @@ int g3c_nccl_unique_id(void* out128) {
 }
 
 int g3c_dit_enable_cp(g3c_dit_t* h, const void* nccl_unique_id, int cp_rank, int cp_size) {
-  G3C_REQUIRE(h && nccl_unique_id && cp_size >= 1 && cp_rank >= 0 && cp_rank < cp_size, "enable_cp: bad arguments");
-  if (!nccl().ok) {
-    set_error("libnccl.so.2 could not be loaded");
-    return G3C_ENCCL;
-  }
-  if (h->comm) {
+  G3C_REQUIRE(h && cp_size >= 1 && cp_size <= 8 && cp_rank >= 0 && cp_rank < cp_size, "enable_cp: bad arguments");
+  if (h->comm && nccl().ok) {
     nccl().CommDestroy(h->comm);
     h->comm = nullptr;
   }
-  ncclUniqueId id;
-  memcpy(&id, nccl_unique_id, 128);
-  G3C_NCCL(nccl().CommInitRank(&h->comm, cp_size, id, cp_rank));
+  h->cp_p2p = nccl_unique_id == nullptr;  // NULL id: fused peer-memory mode (default); else NCCL all-gather mode
+  if (!h->cp_p2p) {
+    if (!nccl().ok) {
+      set_error("libnccl.so.2 could not be loaded");
+      return G3C_ENCCL;
+    }
+    ncclUniqueId id;
+    memcpy(&id, nccl_unique_id, 128);
+    G3C_NCCL(nccl().CommInitRank(&h->comm, cp_size, id, cp_rank));
+  }
   if (!h->comm_stream) G3C_CUDA(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
   if (!h->ev_kv) G3C_CUDA(cudaEventCreateWithFlags(&h->ev_kv, cudaEventDisableTiming));
   if (!h->ev_gathered) G3C_CUDA(cudaEventCreateWithFlags(&h->ev_gathered, cudaEventDisableTiming));
@@ -448,6 +517,35 @@ int g3c_dit_enable_cp(g3c_dit_t* h, const void* nccl_unique_id, int cp_rank, int
   free_ws(h);  // shape-dependent buffers change with cp_size
   return G3C_OK;
 }
+
+int g3c_dit_cp_export(g3c_dit_t* h, void* out_handle64) {
+  G3C_REQUIRE(h && out_handle64, "cp_export: null argument");
+  G3C_REQUIRE(h->cp_region, "cp_export: no context-parallel region (enable_cp without NCCL id, then set_shape)");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t hd;
+  G3C_CUDA(cudaIpcGetMemHandle(&hd, h->cp_region));
+  memcpy(out_handle64, &hd, 64);
+  return G3C_OK;
+}
+
+int g3c_dit_cp_import(g3c_dit_t* h, const void* handles, int n) {
+  G3C_REQUIRE(h && handles && n == h->cp_size, "cp_import: need one 64-byte handle per rank (%d)", h ? h->cp_size : 0);
+  G3C_REQUIRE(h->cp_region, "cp_import: no context-parallel region");
+  for (int r = 0; r < n; ++r) {
+    if (r == h->cp_rank) {
+      h->peer_base[r] = h->cp_region;
+      continue;
+    }
+    if (h->peer_base[r]) continue;
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, (const char*)handles + 64 * r, 64);
+    G3C_CUDA(cudaIpcOpenMemHandle(&h->peer_base[r], hd, cudaIpcMemLazyEnablePeerAccess));
+  }
+  h->peers_open = true;
+  return G3C_OK;
+}
+
+int g3c_dit_cp_mode(const g3c_dit_t* h) { return (h && h->cp_size > 1) ? (h->cp_p2p ? 1 : 2) : 0; }
 
 int g3c_dit_disable_cp(g3c_dit_t* h) {
   G3C_REQUIRE(h, "disable_cp: null handle");
@@ -509,6 +607,25 @@ int g3c_dit_set_shape(g3c_dit_t* h, int T_local, int H_latent, int W_latent, int
     off += align_up(it.bytes, 1024);
   }
   h->ws_bytes = total;
+  if (h->cp_size > 1 && h->cp_p2p) {
+    const size_t set_bytes = align_up((size_t)L * D * 2 * cp, 1024);
+    h->off_k[0] = 0;
+    h->off_k[1] = set_bytes;
+    h->off_vt[0] = 2 * set_bytes;
+    h->off_vt[1] = 3 * set_bytes;
+    h->off_flags = 4 * set_bytes;
+    h->cp_region_bytes = 4 * set_bytes + 1024;
+    e = cudaMalloc(&h->cp_region, h->cp_region_bytes);
+    if (e != cudaSuccess) {
+      h->cp_region = nullptr;
+      set_error("dit_set_shape: cudaMalloc of the %zu-byte context-parallel region failed: %s", h->cp_region_bytes,
+                cudaGetErrorString(e));
+      return G3C_ENOMEM;
+    }
+    G3C_CUDA(cudaMemset(h->cp_region, 0, h->cp_region_bytes));
+    h->peer_base[h->cp_rank] = h->cp_region;
+    h->ws_bytes += h->cp_region_bytes;
+  }
   h->T = T_local;
   h->Hl = H_latent;
   h->Wl = W_latent;

@@ -31,6 +31,8 @@ struct GemmParams {
   const float* gate;   // [N] for EPI_GATED_RESIDUAL
   int num_m_blk, num_n_blk, num_k_blk;
   int super_n;         // n-blocks per super-column (L2 reuse of the B operand)
+  int n_peer;          // bf16 epilogues: additional destinations (peer GPUs), same offsets as D
+  void* peer[7];
 };
 
 template <int BN>
@@ -193,14 +195,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
               if constexpr (EPI == G3C_EPI_GELU_BF16) v[i] = gelu_erf(v[i]);
             }
             if (full_chunk) {
+              uint4 q[4];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                uint4 q;
-                q.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-                q.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-                q.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-                q.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-                reinterpret_cast<uint4*>(dptr)[i] = q;
+                q[i].x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+                q[i].y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+                q[i].z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+                q[i].w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+                reinterpret_cast<uint4*>(dptr)[i] = q[i];
+              }
+              // fused all-gather: the same 64 bytes go to the peers' copies over NVLink (posted writes)
+              for (int pd = 0; pd < p.n_peer; ++pd) {
+                uint4* rp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.peer[pd]) +
+                                                     (size_t)row * p.ldd + col0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rp[i] = q[i];
               }
             } else {
 #pragma unroll
@@ -298,8 +307,10 @@ static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
 
 // Host entry used by the engine and by the C ABI.
 int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
-              int epilogue, const float* gate, int block_n, cudaStream_t st) {
+              int epilogue, const float* gate, int block_n, cudaStream_t st, const PeerDst* peers) {
   G3C_REQUIRE(A && B && D, "gemm: null operand");
+  G3C_REQUIRE(!peers || peers->n == 0 || (epilogue == G3C_EPI_BF16 && N % 32 == 0 && peers->n <= 7),
+              "gemm: peer destinations need the bf16 epilogue, N %% 32 == 0 and at most 7 peers");
   G3C_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape %dx%dx%d", M, N, K);
   G3C_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "gemm: K/lda/ldb must be multiples of 8");
   G3C_REQUIRE(lda >= K && ldb >= K && ldd >= N, "gemm: leading dimension smaller than extent");
@@ -342,6 +353,8 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int ld
   p.ldd = ldd;
   p.D = D;
   p.gate = gate;
+  p.n_peer = peers ? peers->n : 0;
+  for (int i = 0; i < 7; ++i) p.peer[i] = (peers && i < peers->n) ? peers->ptr[i] : nullptr;
   p.num_m_blk = (M + BM - 1) / BM;
   p.num_n_blk = (N + bn - 1) / bn;
   p.num_k_blk = (K + BK - 1) / BK;
@@ -364,5 +377,5 @@ extern "C" int g3c_gemm_bf16(const void* A, const void* B, void* D, int M, int N
                              int ldb, int ldd, int epilogue, const float* gate, int block_n,
                              void* stream) {
   return g3c::gemm_bf16(A, B, D, M, N, K, lda, ldb, ldd, epilogue, gate, block_n,
-                        (cudaStream_t)stream);
+                        (cudaStream_t)stream, nullptr);
 }

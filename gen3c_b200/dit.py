@@ -167,7 +167,19 @@ class VideoExtendGeneralDIT(nn.Module):
     def _set_shape(self, T: int, H: int, W: int, ctx_len: int, fps: float):
         key = (T, H, W, ctx_len, fps)
         if key != self._shape_key:
-            _lib.check(_lib.load().g3c_dit_set_shape(self._engine(), T, H, W, ctx_len, fps), "g3c_dit_set_shape")
+            lib = _lib.load()
+            _lib.check(lib.g3c_dit_set_shape(self._engine(), T, H, W, ctx_len, fps), "g3c_dit_set_shape")
+            if self.cp_group is not None and lib.g3c_dit_cp_mode(self._engine()) == 1:
+                # fused peer-memory mode: exchange the IPC handles of the per-rank K / V^T regions (collective)
+                import torch.distributed as dist
+
+                buf = (C.c_uint8 * 64)()
+                _lib.check(lib.g3c_dit_cp_export(self._engine(), buf), "g3c_dit_cp_export")
+                mine = torch.tensor(list(buf), dtype=torch.uint8, device="cuda")
+                allh = [torch.empty_like(mine) for _ in range(self._cp_size)]
+                dist.all_gather(allh, mine, group=self.cp_group)
+                raw = bytes(torch.cat(allh).cpu().tolist())
+                _lib.check(lib.g3c_dit_cp_import(self._engine(), raw, self._cp_size), "g3c_dit_cp_import")
             self._shape_key = key
 
     def __del__(self):
@@ -184,19 +196,28 @@ class VideoExtendGeneralDIT(nn.Module):
     def is_context_parallel_enabled(self) -> bool:
         return self.cp_group is not None
 
-    def enable_context_parallel(self, cp_group):
+    def enable_context_parallel(self, cp_group, mode: Optional[str] = None):
+        """mode "p2p" (default; env G3C_CP_MODE): K / V^T projections store straight into every rank's buffers over
+        NVLink peer memory; "nccl": one ncclAllGather of K and of V^T per layer (the baseline)."""
+        import os
+
         import torch.distributed as dist
 
+        mode = mode or os.environ.get("G3C_CP_MODE", "p2p")
         rank, size = dist.get_rank(cp_group), dist.get_world_size(cp_group)
         lib = _lib.load()
-        uid = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            buf = (C.c_uint8 * 128)()
-            _lib.check(lib.g3c_nccl_unique_id(buf), "g3c_nccl_unique_id")
-            uid = torch.tensor(list(buf), dtype=torch.uint8)
-        uid = uid.cuda()
-        dist.broadcast(uid, src=dist.get_global_rank(cp_group, 0), group=cp_group)
-        raw = bytes(uid.cpu().tolist())
+        raw = None
+        if mode == "nccl":
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                buf = (C.c_uint8 * 128)()
+                _lib.check(lib.g3c_nccl_unique_id(buf), "g3c_nccl_unique_id")
+                uid = torch.tensor(list(buf), dtype=torch.uint8)
+            uid = uid.cuda()
+            dist.broadcast(uid, src=dist.get_global_rank(cp_group, 0), group=cp_group)
+            raw = bytes(uid.cpu().tolist())
+        elif mode != "p2p":
+            raise ValueError(f"unknown context-parallel mode {mode!r}")
         _lib.check(lib.g3c_dit_enable_cp(self._engine(), raw, rank, size), "g3c_dit_enable_cp")
         self.cp_group, self._cp_rank, self._cp_size = cp_group, rank, size
         self._shape_key = None

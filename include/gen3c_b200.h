@@ -153,7 +153,15 @@ int g3c_dit_load(g3c_dit_t* h, const char* name, const void* ptr, const int64_t*
 /* Context parallelism over the latent-frame axis (reference: general_dit.py:524-543 +
  * module/parallel.py:25-87).  nccl_unique_id: 128 bytes from g3c_nccl_unique_id on rank 0. */
 int g3c_nccl_unique_id(void* out128);
+/* nccl_unique_id == NULL selects the default mode: the K / V^T projections store their tiles straight into every
+ * rank's buffers through NVLink peer memory (fused compute -> all-gather) and attention consumes the chunks as
+ * their arrival flags are raised.  After g3c_dit_set_shape every rank exports the IPC handle of its region
+ * (g3c_dit_cp_export, 64 bytes) and imports the handles of all ranks in rank order (g3c_dit_cp_import).
+ * A non-NULL id selects the baseline mode: one in-place ncclAllGather of K and of V^T per layer. */
 int g3c_dit_enable_cp(g3c_dit_t* h, const void* nccl_unique_id, int cp_rank, int cp_size);
+int g3c_dit_cp_export(g3c_dit_t* h, void* out_handle64);
+int g3c_dit_cp_import(g3c_dit_t* h, const void* handles, int n);
+int g3c_dit_cp_mode(const g3c_dit_t* h); /* 0 = off, 1 = peer-memory (fused), 2 = NCCL */
 int g3c_dit_disable_cp(g3c_dit_t* h);
 
 /* Fix the token grid: T_local latent frames on this rank (of T_local*cp_size), latent H x W,

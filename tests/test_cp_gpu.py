@@ -10,7 +10,7 @@ from oracle import cases, dit_oracle
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, T, H, W, M, ret):
+def _worker(rank, world, port, T, H, W, M, ret, mode):
     import torch.distributed as dist
 
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -24,7 +24,7 @@ def _worker(rank, world, port, T, H, W, M, ret):
         cfg = cases.TINY
         sd = dit_oracle.random_state_dict(cfg, seed=3)
         net = build_net(cfg, sd)
-        net.enable_context_parallel(dist.group.WORLD)
+        net.enable_context_parallel(dist.group.WORLD, mode=mode)
         inp = cases.dit_inputs(cfg, T, H, W, M, seed=5)
         bf = torch.bfloat16
         x_local = split_inputs_cp(inp["x"][None].cuda().to(bf), 2, dist.group.WORLD)
@@ -43,7 +43,10 @@ def _worker(rank, world, port, T, H, W, M, ret):
 
 
 @pytest.mark.timeout(600)
-def test_context_parallel_cp2_matches_oracle():
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+def test_context_parallel_cp2_matches_oracle(mode):
+    """p2p: projections store K / V^T straight into the peer's buffers (fused compute -> all-gather, chunk-gated
+    attention); nccl: the ncclAllGather baseline.  Both must equal the single-device oracle."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -55,8 +58,8 @@ def test_context_parallel_cp2_matches_oracle():
     want = dit_oracle.forward(sd, cfg, inp["x"], inp["cond_mask"], inp["pose"], inp["padding"], inp["timestep"], inp["ctx_c"])
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, T, H, W, M, ret)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + (7 if mode == "nccl" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, T, H, W, M, ret, mode)) for r in range(2)]
     for p in procs:
         p.start()
     got = ret.get(timeout=400)
@@ -64,5 +67,5 @@ def test_context_parallel_cp2_matches_oracle():
         p.join(timeout=60)
         assert p.exitcode == 0
     rel = float((got - want).norm() / want.norm())
-    print("cp2 rel-L2 vs oracle", rel)
+    print(f"cp2 [{mode}] rel-L2 vs oracle", rel)
     assert rel < 5e-3
