@@ -13,6 +13,7 @@
 //   warp 2      TMEM allocator
 //   warps 4-7   epilogue       : tcgen05.ld (lane = row) -> fused epilogue -> global
 // Two TMEM accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cstdlib>
 #include <cstring>
 
 #include "kernels.h"
@@ -67,6 +68,91 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& 
     n_blk = n0 + rem - m_blk * p.super_n;
   }
 }
+
+// One 32-column chunk of the epilogue for the 32 rows of a warp (lane = row).  `row0w` = first row of the warp.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const uint32_t (&r)[32], const GemmParams& p, const CUtensorMap* tmD_ptr,
+                                               int row0w, int col0, uint32_t lane, uint8_t* stage_warp,
+                                               uint32_t& ebuf) {
+  const int row = row0w + (int)lane;
+  const bool row_ok = row < p.M;
+        if constexpr (EPI == G3C_EPI_BF16 || EPI == G3C_EPI_GELU_BF16) {
+          // lane = row: each thread stores 64 contiguous bytes of its own row (full 32-B sectors)
+          if (row_ok && col0 < p.N) {
+            const bool full_chunk = col0 + 32 <= p.N;
+            __nv_bfloat16* dptr = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col0;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              v[i] = __uint_as_float(r[i]);
+              if constexpr (EPI == G3C_EPI_GELU_BF16) v[i] = gelu_erf(v[i]);
+            }
+            if (full_chunk) {
+              uint4 q[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                q[i].x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
+                q[i].y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+                q[i].z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
+                q[i].w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+                reinterpret_cast<uint4*>(dptr)[i] = q[i];
+              }
+              // fused all-gather: the same 64 bytes go to the peers' copies over NVLink (posted writes)
+#pragma unroll
+              for (int pd = 0; pd < 7; ++pd) {
+                if (pd < p.n_peer) {
+                  uint4* rp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.peer[pd]) +
+                                                       (size_t)row * p.ldd + col0);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) rp[i] = q[i];
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) dptr[i] = __float2bfloat16_rn(v[i]);
+            }
+          }
+        } else {
+          // fp32 output / gated residual: the 32x32 fp32 chunk goes to a 128-byte-swizzled shared tile and one
+          // elected lane hands it to the TMA: plain store, or reduce-add into the fp32 residual stream in L2
+          // (x += gate * acc without ever loading x into the SM).  TMA clips rows >= M / columns >= N.
+          if (col0 < p.N) {  // warp-uniform
+            uint8_t* stg = stage_warp + (ebuf & 1) * 4096;
+            if (lane == 0) tma_store_wait_read<1>();  // the store that last used this buffer has read it
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                     __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+              if constexpr (EPI == G3C_EPI_GATED_RESIDUAL_F32) {
+                const int cg = col0 + 4 * j;
+                float4 g;
+                if (cg + 4 <= p.N) {
+                  g = *reinterpret_cast<const float4*>(p.gate + cg);
+                } else {  // ragged right edge: columns >= N are clipped by the TMA
+                  g.x = cg + 0 < p.N ? p.gate[cg + 0] : 0.f;
+                  g.y = cg + 1 < p.N ? p.gate[cg + 1] : 0.f;
+                  g.z = cg + 2 < p.N ? p.gate[cg + 2] : 0.f;
+                  g.w = 0.f;
+                }
+                v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+              }
+              // row = lane, 16-byte chunk j -> swizzled chunk j ^ (row % 8)
+              *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              const int row0 = row0w;
+              if constexpr (EPI == G3C_EPI_GATED_RESIDUAL_F32) tma_reduce_add_2d(tmD_ptr, stg, col0, row0);
+              else tma_store_2d(tmD_ptr, stg, col0, row0);
+              tma_store_commit();
+            }
+            ++ebuf;
+          }
+        }
+      }
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -175,87 +261,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       tile_coords(p, tile, m_blk, n_blk);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const int row = m_blk * BM + ew * 32 + lane;
-      const bool row_ok = row < p.M;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((ew * 32u) << 16) + as * BN + c * 32, r);
         tc_wait_ld();
-        const int col0 = n_blk * BN + c * 32;
-        if constexpr (EPI == G3C_EPI_BF16 || EPI == G3C_EPI_GELU_BF16) {
-          // lane = row: each thread stores 64 contiguous bytes of its own row (full 32-B sectors)
-          if (row_ok && col0 < p.N) {
-            const bool full_chunk = col0 + 32 <= p.N;
-            __nv_bfloat16* dptr = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col0;
-            float v[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              v[i] = __uint_as_float(r[i]);
-              if constexpr (EPI == G3C_EPI_GELU_BF16) v[i] = gelu_erf(v[i]);
-            }
-            if (full_chunk) {
-              uint4 q[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                q[i].x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]);
-                q[i].y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
-                q[i].z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]);
-                q[i].w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-                reinterpret_cast<uint4*>(dptr)[i] = q[i];
-              }
-              // fused all-gather: the same 64 bytes go to the peers' copies over NVLink (posted writes)
-              for (int pd = 0; pd < p.n_peer; ++pd) {
-                uint4* rp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.peer[pd]) +
-                                                     (size_t)row * p.ldd + col0);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) rp[i] = q[i];
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) dptr[i] = __float2bfloat16_rn(v[i]);
-            }
-          }
-        } else {
-          // fp32 output / gated residual: the 32x32 fp32 chunk goes to a 128-byte-swizzled shared tile and one
-          // elected lane hands it to the TMA: plain store, or reduce-add into the fp32 residual stream in L2
-          // (x += gate * acc without ever loading x into the SM).  TMA clips rows >= M / columns >= N.
-          if (col0 < p.N) {  // warp-uniform
-            uint8_t* stg = stage_f32 + (ew * 2 + (ebuf & 1)) * 4096;
-            if (lane == 0) tma_store_wait_read<1>();  // the store that last used this buffer has read it
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                     __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-              if constexpr (EPI == G3C_EPI_GATED_RESIDUAL_F32) {
-                const int cg = col0 + 4 * j;
-                float4 g;
-                if (cg + 4 <= p.N) {
-                  g = *reinterpret_cast<const float4*>(p.gate + cg);
-                } else {  // ragged right edge: columns >= N are clipped by the TMA
-                  g.x = cg + 0 < p.N ? p.gate[cg + 0] : 0.f;
-                  g.y = cg + 1 < p.N ? p.gate[cg + 1] : 0.f;
-                  g.z = cg + 2 < p.N ? p.gate[cg + 2] : 0.f;
-                  g.w = 0.f;
-                }
-                v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
-              }
-              // row = lane, 16-byte chunk j -> swizzled chunk j ^ (row % 8)
-              *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = v;
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-              const int row0 = m_blk * BM + ew * 32;
-              if constexpr (EPI == G3C_EPI_GATED_RESIDUAL_F32) tma_reduce_add_2d(&tmD, stg, col0, row0);
-              else tma_store_2d(&tmD, stg, col0, row0);
-              tma_store_commit();
-            }
-            ++ebuf;
-          }
-        }
+        epilogue_chunk<EPI>(r, p, &tmD, m_blk * BM + (int)ew * 32, n_blk * BN + c * 32, lane,
+                            stage_f32 + ew * 2 * 4096, ebuf);
       }
       tc_fence_before();
       mbar_arrive(&tempty[as]);
@@ -273,6 +285,189 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// CTA-pair variant: 256 x 256 output tile per cluster of two CTAs (`tcgen05.mma.cta_group::2`, UMMA M = 256).
+// Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 rows of W); the tensor cores of both
+// SMs read both halves, so the shared-memory operand traffic per MMA drops from 12 KB to 8 KB per SM — the
+// single-CTA kernel above is bound there (ncu: l1tex 75 %, tensor pipe 78 %, profiles/r01_gemm_ncu_summary.txt).
+// Barriers: `full` lives in the leader (count 2: its own expect_tx arrive + the peer's remote arrive, both CTAs'
+// TMA bytes are credited to it); `empty` / `tfull` exist in both CTAs and are hit by multicast commits;
+// `tempty` lives in the leader and collects one elected arrive per epilogue warp of both CTAs.
+// ------------------------------------------------------------------------------------------------------------
+struct Gemm2Smem {
+  static constexpr int kStages = 6;
+  static constexpr int kABytes = 128 * BK * 2;   // 16 KB: this CTA's 128 rows of A
+  static constexpr int kBBytes = 128 * BK * 2;   // 16 KB: this CTA's half of the 256-row B tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStageF32 = 4 * 2 * 4096;
+  static constexpr int kTotal = kStages * kStageBytes + kStageF32 + 256 + 1024;
+};
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    k_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
+  using S = Gemm2Smem;
+  constexpr int kStages = S::kStages;
+  constexpr int BN2 = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * S::kABytes;
+  uint8_t* stage_f32 = smem + kStages * S::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_f32 + S::kStageF32);
+  uint64_t* full = bars;                      // [kStages] (used in the leader)
+  uint64_t* empty = bars + kStages;           // [kStages] (both CTAs)
+  uint64_t* tfull = bars + 2 * kStages;       // [2]       (both CTAs)
+  uint64_t* tempty = bars + 2 * kStages + 2;  // [2]       (used in the leader)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+  const uint32_t cta = cluster_ctarank();
+  const bool leader = cta == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 2);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_ptr, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_tiles = p.num_m_blk * p.num_n_blk;  // num_m_blk counts 256-row blocks here
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs) =====
+      uint32_t stage = 0, phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        int m_blk, n_blk;
+        tile_coords(p, tile, m_blk, n_blk);
+        for (int kb = 0; kb < p.num_k_blk; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&full[stage], 2 * S::kStageBytes);
+          else mbar_arrive_leader(&full[stage]);
+          tma_load_2d_2sm(smem_a + stage * S::kABytes, &tmA, &full[stage], kb * BK, m_blk * 256 + (int)cta * 128);
+          tma_load_2d_2sm(smem_b + stage * S::kBBytes, &tmB, &full[stage], kb * BK, n_blk * BN2 + (int)cta * 128);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ===== MMA issuer (one thread of the leader CTA) =====
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN2);
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN2;
+        for (int kb = 0; kb < p.num_k_blk; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_sdesc_sw128(smem_u32(smem_a + stage * S::kABytes));
+          const uint64_t db = make_sdesc_sw128(smem_u32(smem_b + stage * S::kBBytes));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            umma_ss_2sm(d_tmem, sdesc_advance(da, k * UMMA_K * 2), sdesc_advance(db, k * UMMA_K * 2), idesc,
+                        (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tfull[as]);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs, each for its own 128 rows) =====
+    const uint32_t ew = warp - 4;
+    uint32_t as = 0, aphase = 0, ebuf = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+      int m_blk, n_blk;
+      tile_coords(p, tile, m_blk, n_blk);
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN2 / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((ew * 32u) << 16) + as * BN2 + c * 32, r);
+        tc_wait_ld();
+        epilogue_chunk<EPI>(r, p, &tmD, m_blk * 256 + (int)cta * 128 + (int)ew * 32, n_blk * BN2 + c * 32, lane,
+                            stage_f32 + ew * 2 * 4096, ebuf);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tempty[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer's tensor core may still read this CTA's shared memory until both are done
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+template <int EPI>
+static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                        const GemmParams& p, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    G3C_CUDA(cudaFuncSetAttribute(k_gemm2<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Smem::kTotal));
+    configured = true;
+  }
+  int tiles = p.num_m_blk * p.num_n_blk;
+  int clusters = sm_count() / 2;
+  if (tiles < clusters) clusters = tiles;
+  k_gemm2<EPI><<<2 * clusters, GEMM_THREADS, Gemm2Smem::kTotal, st>>>(tmA, tmB, tmD, p);
+  G3C_CUDA(cudaGetLastError());
+  return G3C_OK;
+}
+
+static int dispatch_epi2(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                         const GemmParams& p, cudaStream_t st) {
+  switch (epi) {
+    case G3C_EPI_BF16: return launch_gemm2<G3C_EPI_BF16>(tmA, tmB, tmD, p, st);
+    case G3C_EPI_GELU_BF16: return launch_gemm2<G3C_EPI_GELU_BF16>(tmA, tmB, tmD, p, st);
+    case G3C_EPI_GATED_RESIDUAL_F32: return launch_gemm2<G3C_EPI_GATED_RESIDUAL_F32>(tmA, tmB, tmD, p, st);
+    case G3C_EPI_F32: return launch_gemm2<G3C_EPI_F32>(tmA, tmB, tmD, p, st);
+  }
+  set_error("gemm: unknown epilogue %d", epi);
+  return G3C_EINVAL;
 }
 
 template <int BN, int EPI>
@@ -324,16 +519,29 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int ld
                   (gate && (reinterpret_cast<uintptr_t>(gate) & 15) == 0),
               "gemm: gated-residual epilogue needs a 16-byte aligned gate vector");
   int bn = block_n;
+  static int pair_default = -1;
+  if (pair_default < 0) {
+    const char* e = getenv("G3C_GEMM_2CTA");
+    pair_default = e ? atoi(e) : 0;
+  }
+  // block_n 512 = CTA-pair kernel (256 x 256 tile over two SMs); chosen automatically for large, aligned problems
+  // when G3C_GEMM_2CTA=1
+  if (bn == 0 && pair_default && N % 256 == 0 && M >= 1024 && K >= 256) bn = 512;
   if (bn == 0) bn = (N >= 256 && N % 256 == 0) ? 256 : (N > 64 ? 128 : 64);
-  G3C_REQUIRE(bn == 64 || bn == 128 || bn == 256, "gemm: block_n %d unsupported", bn);
+  G3C_REQUIRE(bn == 64 || bn == 128 || bn == 256 || bn == 512, "gemm: block_n %d unsupported", bn);
+  const bool pair = bn == 512;
+  if (pair) {
+    G3C_REQUIRE(N % 256 == 0, "gemm: the CTA-pair kernel needs N %% 256 == 0 (N=%d)", N);
+    bn = 256;
+  }
 
   CUtensorMap tmA, tmB;
   uint64_t dimsA[2] = {(uint64_t)K, (uint64_t)M}, strA[1] = {(uint64_t)lda * 2};
-  uint32_t boxA[2] = {BK, BM};
+  uint32_t boxA[2] = {BK, 128};
   int rc = make_tmap_bf16_sw128(&tmA, A, 2, dimsA, strA, boxA);
   if (rc) return rc;
   uint64_t dimsB[2] = {(uint64_t)K, (uint64_t)N}, strB[1] = {(uint64_t)ldb * 2};
-  uint32_t boxB[2] = {BK, (uint32_t)bn};
+  uint32_t boxB[2] = {BK, (uint32_t)(pair ? 128 : bn)};
   rc = make_tmap_bf16_sw128(&tmB, B, 2, dimsB, strB, boxB);
   if (rc) return rc;
 
@@ -355,7 +563,7 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int ld
   p.gate = gate;
   p.n_peer = peers ? peers->n : 0;
   for (int i = 0; i < 7; ++i) p.peer[i] = (peers && i < peers->n) ? peers->ptr[i] : nullptr;
-  p.num_m_blk = (M + BM - 1) / BM;
+  p.num_m_blk = pair ? (M + 255) / 256 : (M + BM - 1) / BM;
   p.num_n_blk = (N + bn - 1) / bn;
   p.num_k_blk = (K + BK - 1) / BK;
   // keep one super-column of B (super_n * bn * K * 2 bytes) well inside the 126 MB L2
@@ -364,6 +572,7 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int ld
   if (sn < 1) sn = 1;
   if (sn > p.num_n_blk) sn = p.num_n_blk;
   p.super_n = sn;
+  if (pair) return dispatch_epi2(epilogue, tmA, tmB, tmD, p, st);
   switch (bn) {
     case 64: return dispatch_epi<64>(epilogue, tmA, tmB, tmD, p, st);
     case 128: return dispatch_epi<128>(epilogue, tmA, tmB, tmD, p, st);

@@ -32,6 +32,23 @@ def test_gemm_bf16(M, N, K, bn):
     assert rel(out32, ref) < 1e-5, rel(out32, ref)
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 512, 4096), (1000, 4096, 1024), (4096, 7168, 256), (128, 256, 512),
+                                   (7040, 4096, 4096)])
+def test_gemm_cta_pair(M, N, K):
+    """CTA-pair kernel (tcgen05.mma.cta_group::2, 256 x 256 tile over two SMs), selected with block_n = 512."""
+    from gen3c_b200 import ops
+
+    a, b = bf(M, K, seed=21), bf(N, K, seed=22, s=0.05)
+    ref = a.float() @ b.float().T
+    assert rel(ops.gemm(a, b, ops.EPI_BF16, block_n=512), ref) < 3e-3
+    assert rel(ops.gemm(a, b, ops.EPI_F32, block_n=512), ref) < 1e-5
+    x = torch.randn(M, N, device="cuda")
+    gate = torch.randn(N, device="cuda")
+    got = ops.gemm(a, b, ops.EPI_GATED_RESIDUAL_F32, out=x.clone(), gate=gate, block_n=512)
+    assert rel(got, x + gate * ref) < 1e-5
+    assert rel(ops.gemm(a, b, ops.EPI_GELU_BF16, block_n=512), torch.nn.functional.gelu(ref)) < 3e-3
+
+
 def test_gemm_epilogues():
     from gen3c_b200 import ops
 
