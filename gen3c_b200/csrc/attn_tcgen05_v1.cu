@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         int chunk = p.first_chunk + j / tiles_per_chunk;
         if (chunk >= n_chunks) chunk -= n_chunks;
         const int within = j % tiles_per_chunk;
-        if (p.chunk_flags && within == 0) {
+        if (p.chunk_flags && within == 0 && chunk != p.first_chunk) {  // the local chunk is ordered by the stream
           uint32_t v, spins = 0;
           uint64_t t0 = 0;
           for (;;) {

@@ -112,10 +112,14 @@ __global__ void __launch_bounds__(256)
   *reinterpret_cast<__nv_bfloat162*>(p + 64 + 2 * lane) = o1;
   // fused all-gather of the normalised keys: same offsets in the peers' buffers (NVLink posted writes)
   const size_t off = (size_t)tok * ld + head * 128;
-  for (int i = 0; i < peers.n; ++i) {
-    __nv_bfloat16* r = reinterpret_cast<__nv_bfloat16*>(peers.ptr[i]) + off;
-    *reinterpret_cast<__nv_bfloat162*>(r + 2 * lane) = o0;
-    *reinterpret_cast<__nv_bfloat162*>(r + 64 + 2 * lane) = o1;
+  // (static indices only: a dynamically indexed kernel parameter would be copied to local memory by every thread)
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    if (i < peers.n) {
+      __nv_bfloat16* r = reinterpret_cast<__nv_bfloat16*>(peers.ptr[i]) + off;
+      *reinterpret_cast<__nv_bfloat162*>(r + 2 * lane) = o0;
+      *reinterpret_cast<__nv_bfloat162*>(r + 64 + 2 * lane) = o1;
+    }
   }
 }
 

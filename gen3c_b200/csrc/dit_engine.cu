@@ -19,6 +19,7 @@
 
 #include <array>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -113,6 +114,7 @@ struct g3c_dit {
   // default CP mode: fused projection -> all-gather through NVLink peer memory.  One cudaMalloc'd region per
   // rank, IPC-mapped by every peer: K / V^T of all ranks, double buffered by layer parity, plus arrival flags.
   bool cp_p2p = true;
+  bool cp_push_sm = false;  // G3C_CP_PUSH=sm: peer stores from the producing kernels; default: copy engines
   void* cp_region = nullptr;
   size_t cp_region_bytes = 0, off_k[2] = {0, 0}, off_vt[2] = {0, 0}, off_flags = 0;
   void* peer_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -350,12 +352,31 @@ static int forward(g3c_dit* h, const void* x_in, const void* cond_mask, const vo
           pk.ptr[pk.n++] = pb + h->off_k[set] + (size_t)me * slice;
           pv.ptr[pv.n++] = pb + h->off_vt[set] + (size_t)me * slice;
         }
-        K(CAT_GEMM, gemm_bf16(h->xn, s.wk, kl, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
-        K(CAT_COMM, rmsnorm_rope(kl, D, L, heads, s.gk, h->rope, 1e-6f, st, &pk));
-        K(CAT_COMM, gemm_bf16(s.wv, h->xn, vl, D, L, D, D, D, L, G3C_EPI_BF16, nullptr, 0, st, &pv));  // V^T
-        k_cp_signal<<<1, 32, 0, st>>>(pf, seq);
-        G3C_CUDA(cudaGetLastError());
-        ++n;
+        if (h->cp_push_sm) {
+          // variant A (G3C_CP_PUSH=sm): the producing kernels themselves store every tile to all peers
+          K(CAT_GEMM, gemm_bf16(h->xn, s.wk, kl, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
+          K(CAT_COMM, rmsnorm_rope(kl, D, L, heads, s.gk, h->rope, 1e-6f, st, &pk));
+          K(CAT_COMM, gemm_bf16(s.wv, h->xn, vl, D, L, D, D, D, L, G3C_EPI_BF16, nullptr, 0, st, &pv));  // V^T
+          k_cp_signal<<<1, 32, 0, st>>>(pf, seq);
+          G3C_CUDA(cudaGetLastError());
+          ++n;
+        } else {
+          // default: produce locally, then the copy engines push the two slices to every peer on a side stream while
+          // this stream already runs the Q projection and attention over the local chunk; the flag that opens a
+          // remote chunk on a peer is raised (system scope) after all of this rank's copies have completed.
+          K(CAT_GEMM, gemm_bf16(h->xn, s.wk, kl, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
+          K(CAT_ELTWISE, rmsnorm_rope(kl, D, L, heads, s.gk, h->rope, 1e-6f, st));
+          K(CAT_GEMM, gemm_bf16(s.wv, h->xn, vl, D, L, D, D, D, L, G3C_EPI_BF16, nullptr, 0, st));  // V^T
+          G3C_CUDA(cudaEventRecord(h->ev_kv, st));
+          G3C_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_kv, 0));
+          for (int i2 = 0; i2 < pk.n; ++i2) {
+            G3C_CUDA(cudaMemcpyAsync(pk.ptr[i2], kl, slice, cudaMemcpyDeviceToDevice, h->comm_stream));
+            G3C_CUDA(cudaMemcpyAsync(pv.ptr[i2], vl, slice, cudaMemcpyDeviceToDevice, h->comm_stream));
+          }
+          k_cp_signal<<<1, 32, 0, h->comm_stream>>>(pf, seq);
+          G3C_CUDA(cudaGetLastError());
+          n += 2 * pk.n + 1;
+        }
         K(CAT_GEMM, gemm_bf16(h->xn, s.wq, h->q, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
         K(CAT_ELTWISE, rmsnorm_rope(h->q, D, L, heads, s.gq, h->rope, 1e-6f, st));
         ChunkGate gate;
@@ -500,6 +521,10 @@ int g3c_dit_enable_cp(g3c_dit_t* h, const void* nccl_unique_id, int cp_rank, int
     h->comm = nullptr;
   }
   h->cp_p2p = nccl_unique_id == nullptr;  // NULL id: fused peer-memory mode (default); else NCCL all-gather mode
+  {
+    const char* e = getenv("G3C_CP_PUSH");
+    h->cp_push_sm = e && e[0] == 's';
+  }
   if (!h->cp_p2p) {
     if (!nccl().ok) {
       set_error("libnccl.so.2 could not be loaded");

@@ -522,10 +522,10 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int ld
   static int pair_default = -1;
   if (pair_default < 0) {
     const char* e = getenv("G3C_GEMM_2CTA");
-    pair_default = e ? atoi(e) : 0;
+    pair_default = e ? atoi(e) : 1;
   }
   // block_n 512 = CTA-pair kernel (256 x 256 tile over two SMs); chosen automatically for large, aligned problems
-  // when G3C_GEMM_2CTA=1
+  // (G3C_GEMM_2CTA=0 disables it)
   if (bn == 0 && pair_default && N % 256 == 0 && M >= 1024 && K >= 256) bn = 512;
   if (bn == 0) bn = (N >= 256 && N % 256 == 0) ? 256 : (N > 64 ? 128 : 64);
   G3C_REQUIRE(bn == 64 || bn == 128 || bn == 256 || bn == 512, "gemm: block_n %d unsupported", bn);
