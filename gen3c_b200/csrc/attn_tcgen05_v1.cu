@@ -1,5 +1,5 @@
-// Path D — attention forward, round-1 baseline kernel (kept selectable with G3C_ATTN_IMPL=v1 for A/B timing):
-// per-tile S buffers with P aliasing S; strict A/B alternation.  See attn_tcgen05.cu for the default kernel.
+// Path D — attention forward, the DEFAULT kernel: per-tile S buffers with P aliasing S, A/B tile alternation.
+// (attn_tcgen05.cu holds the dispatcher and an experimental decoupled-issue variant, G3C_ATTN_IMPL=v4.)
 //   O = softmax(Q K^T * scale) V        (reference: cosmos_predict1/diffusion/module/attention.py
 //   :282-297 `cal_attn` -> transformer_engine DotProductAttention(sbhd, no_mask, dropout 0);
 //   self-attention Lq = Lk = 56 320, cross-attention Lk = 512)
@@ -19,9 +19,14 @@
 // TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,384) O_B [384,512); P (bf16) overwrites
 // the first 64 columns of its S tile and feeds the P·V MMA straight from TMEM.
 // MMA order per KV step j:  PV_A(j) ; S_A(j+1) ; PV_B(j) ; S_B(j+1)  — the S MMA of one tile and
-// the whole PV/S pair of the other overlap with that tile's softmax.
-// Online softmax keeps a lazily updated reference max: O / row-sum are only rescaled when the row
-// max grew by more than 2^8, so the TMEM read-modify-write of O is rare after the first tiles.
+// the whole PV/S pair of the other overlap with that tile's softmax.  P is released to the MMA warp
+// in two 64-key halves, so the first four P·V k-steps run under the second half of the exponentials.
+// Per tile the dependent chain is  S MMA -> softmax -> PV MMA -> (P columns free) -> next S MMA, so
+// the softmax LATENCY of one tile, not its throughput, sets the step period (clock64 timelines:
+// profiles/r01_attn_v1_timeline.txt).  Hence (kMode 1): the row max is reduced in the shadow of the
+// exponentials of the first half, which speculatively use the previous reference max; O / row sum are
+// only rescaled (and that half recomputed) when the max grew past the lazy threshold — rare after
+// the first KV tiles; fp32x2 packed FFMA/FADD and 3-input max halve the non-MUFU issue slots.
 #include <cstdlib>
 
 #include "kernels.h"
@@ -45,6 +50,7 @@ struct AttnParams {
   const uint32_t* chunk_flags;  // context-parallel gate (or NULL): chunk c readable once chunk_flags[c] >= flag_seq
   uint32_t flag_seq;
   int first_chunk;
+  int p_halves;               // 1: P is released to the MMA warp per 64-key half, 0: per 128-key tile
   unsigned long long* trace;  // kTrace only: [3 roles][64 steps][8 slots] clock64 stamps of CTA (0,0)
 };
 
@@ -73,7 +79,60 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
 }
 
-template <int kPolyEvery, bool kTrace>
+// Packed fp32x2 arithmetic (FFMA2 / FADD2) and the 3-input max (FMNMX3) of sm_100: half the issue slots of the
+// scalar forms for the scale-subtract, the row sums and the row max.
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// Exponentials of the 64 keys of half `hh` of one S row: p = 2^(s*c + neg), packed to bf16 pairs, row sums in two
+// packed accumulators.  kMax additionally folds ALL 128 scores of the row into four max chains (two FMNMX3 per
+// iteration), so the row max of this KV tile is reduced in the shadow of the MUFU-bound exponentials.
+template <int kPolyEvery, bool kMax>
+__device__ __forceinline__ void exp_half(const uint32_t (&s)[128], int hh, float c, float neg, uint32_t (&pk)[32],
+                                         uint64_t (&ls2)[2], float (&mxs)[4]) {
+  const uint64_t c2 = pack2(c, c), n2 = pack2(neg, neg);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const uint64_t x2 = ffma2(pack2(__uint_as_float(s[hh * 64 + 2 * i]), __uint_as_float(s[hh * 64 + 2 * i + 1])), c2, n2);
+    float xa, xb;
+    unpack2(x2, xa, xb);
+    const float a = ex2_approx(xa);
+    const float b = (kPolyEvery > 0 && (i % (kPolyEvery / 2 > 0 ? kPolyEvery / 2 : 1)) == 0) ? ex2_poly(xb) : ex2_approx(xb);
+    ls2[i & 1] = fadd2(ls2[i & 1], pack2(a, b));
+    pk[i] = pack_bf16x2(a, b);
+    if constexpr (kMax) {
+      mxs[(2 * i) & 3] = fmax3(mxs[(2 * i) & 3], __uint_as_float(s[4 * i]), __uint_as_float(s[4 * i + 1]));
+      mxs[(2 * i + 1) & 3] = fmax3(mxs[(2 * i + 1) & 3], __uint_as_float(s[4 * i + 2]), __uint_as_float(s[4 * i + 3]));
+    }
+  }
+}
+
+// kMode 0: max -> (lazy rescale) -> exponentials, scalar arithmetic.
+// kMode 1: speculative reference max — the exponentials of the first 64 keys are computed against the PREVIOUS
+//          reference max while this tile's max is reduced; only if the max grew past the lazy-rescale threshold
+//          (rare after the first KV tiles) are they recomputed.  Packed fp32x2 arithmetic.
+template <int kPolyEvery, bool kTrace, int kMode>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
     k_attn_fwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -87,8 +146,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
   uint64_t* kv_full = bars + 1;                   // [slots]
   uint64_t* kv_empty = bars + 1 + ATT_SLOTS;      // [slots]
   uint64_t* s_full = bars + 1 + 2 * ATT_SLOTS;    // [2]
-  uint64_t* p_full = bars + 3 + 2 * ATT_SLOTS;    // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5 + 2 * ATT_SLOTS);
+  uint64_t* p_half = bars + 3 + 2 * ATT_SLOTS;    // [tile][key half]: P columns of 64 keys stored
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7 + 2 * ATT_SLOTS);
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -107,7 +166,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_half[2 * i], 4);      // one elected arrive per softmax warp
+      mbar_init(&p_half[2 * i + 1], 4);
     }
     fence_barrier_init();
   }
@@ -188,10 +248,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           umma_ss(tS[t], sdesc_advance(da, off), sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
         }
       };
-      auto mma_pv = [&](int t, uint32_t vslot, bool first) {
-        // O_t += P_t V : 8 k-steps over the 128 keys; A = P from TMEM (bf16 pairs per column)
+      auto mma_pv = [&](int t, uint32_t vslot, bool first, int hh) {
+        // O_t += P_t V for the 64 keys of half hh: 4 k-steps; A = P from TMEM (bf16 pairs per column)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = hh * 4 + kk;
           const uint32_t half = k >> 2, off = (k & 3) * 32;
           uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + vslot * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
           umma_ts(tO[t], tS[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
@@ -214,10 +275,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         advance();
         // ---- tile A
         ATT_TR(0, 0);
-        mbar_wait(&p_full[0], j & 1);
+        // the P·V MMAs of the first 64 keys start while the softmax still exponentiates the second 64
+        mbar_wait(&p_half[0], j & 1);
         ATT_TR(0, 1);
         tc_fence_after();
-        mma_pv(0, vslot, j == 0);
+        mma_pv(0, vslot, j == 0, 0);
+        mbar_wait(&p_half[1], j & 1);
+        tc_fence_after();
+        mma_pv(0, vslot, j == 0, 1);
         if (more) {
           mbar_wait(&kv_full[slot], phase);  // K_{j+1}
           tc_fence_after();
@@ -228,10 +293,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         umma_commit(&s_full[0]);
         ATT_TR(0, 2);
         // ---- tile B
-        mbar_wait(&p_full[1], j & 1);
+        mbar_wait(&p_half[2], j & 1);
         ATT_TR(0, 3);
         tc_fence_after();
-        mma_pv(1, vslot, j == 0);
+        mma_pv(1, vslot, j == 0, 0);
+        mbar_wait(&p_half[3], j & 1);
+        tc_fence_after();
+        mma_pv(1, vslot, j == 0, 1);
         umma_commit(&kv_empty[vslot]);
         if (more) {
           mma_s(1, kslot);
@@ -250,7 +318,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     const uint32_t tS = tmem_base + lane_base + t * 128;
     const uint32_t tO = tmem_base + lane_base + 256 + t * 128;
     const float c = p.scale_log2;
-    float m_used = 0.0f;  // reference max (raw score units) the stored exponentials are relative to
+    float m_used = kMode == 0 ? 0.0f : -INFINITY;  // reference max (raw score units) the stored exponentials are relative to
     float l = 0.0f;       // running row sum (relative to m_used)
     uint32_t sphase = 0;
     const bool tr = kTrace && (warp & 3) == 0 && lane == 0;
@@ -265,61 +333,122 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       for (int cc = 0; cc < 4; ++cc) tmem_ld32(tS + cc * 32, s + cc * 32);
       tc_wait_ld();
       if (tr) ATT_TR(1 + t, 2);
+      if constexpr (kMode == 0) {
       // 8 independent max chains (a single dependent FMNMX chain costs ~6 clk per link: 400 clk per tile
-      // in the round-1 profile)
-      float mxs[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) mxs[i] = __uint_as_float(s[i]);
-#pragma unroll
-      for (int i = 8; i < 128; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], __uint_as_float(s[i]));
-      const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
-                             fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
-      if (j == 0) {
-        m_used = mx;
+        // in the round-1 profile)
+        float mxs[8];
+  #pragma unroll
+        for (int i = 0; i < 8; ++i) mxs[i] = __uint_as_float(s[i]);
+  #pragma unroll
+        for (int i = 8; i < 128; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], __uint_as_float(s[i]));
+        const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                               fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+        if (j == 0) {
+          m_used = mx;
+        } else {
+          const bool grow = (mx - m_used) * c > 8.0f;
+          if (__any_sync(0xffffffffu, grow)) {
+            // s_full(j) was committed after PV(j-1): O already holds every earlier contribution.
+            const float m_new = fmaxf(m_used, mx);
+            const float alpha = ex2_approx((m_used - m_new) * c);
+            m_used = m_new;
+            l *= alpha;
+  #pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+              uint32_t o[32];
+              tmem_ld32(tO + cc * 32, o);
+              tc_wait_ld();
+  #pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(tO + cc * 32, o);
+            }
+            tc_wait_st();
+          }
+        }
+        const float neg = -m_used * c;
+        if (tr) ATT_TR(1 + t, 3);
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+  #pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t pk[32];
+  #pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float xa = fmaf(__uint_as_float(s[hh * 64 + 2 * i]), c, neg);
+            const float xb = fmaf(__uint_as_float(s[hh * 64 + 2 * i + 1]), c, neg);
+            float a = ex2_approx(xa);
+            float b = (kPolyEvery > 0 && (i % (kPolyEvery / 2 > 0 ? kPolyEvery / 2 : 1)) == 0) ? ex2_poly(xb) : ex2_approx(xb);
+            ls[(2 * i) & 3] += a;
+            ls[(2 * i + 1) & 3] += b;
+            pk[i] = pack_bf16x2(a, b);
+          }
+          tmem_st32(tS + hh * 32, pk);
+          if (p.p_halves || hh == 1) {
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (!p.p_halves) mbar_arrive(&p_half[2 * t]);
+              mbar_arrive(&p_half[2 * t + hh]);
+            }
+          }
+          if (tr && hh == 0) ATT_TR(1 + t, 4);
+        }
+        l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       } else {
-        const bool grow = (mx - m_used) * c > 8.0f;
+        // fp32 keeps the full exponent range in P (bf16) and in O / l, so the rescale threshold only guards
+        // against overflow: 2^24 here (the stored exponentials are <= 2^24, row sums <= 2^24 * Lk).
+        constexpr float kGrow = 24.0f;
+        uint32_t pk[32];
+        uint64_t ls2[2] = {0ull, 0ull};
+        float mxs[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        float neg = -m_used * c;  // j == 0: m_used = -inf, every row takes the slow path below
+        exp_half<kPolyEvery, true>(s, 0, c, neg, pk, ls2, mxs);
+        const float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
+        const bool grow = !((mx - m_used) * c <= kGrow);
         if (__any_sync(0xffffffffu, grow)) {
           // s_full(j) was committed after PV(j-1): O already holds every earlier contribution.
           const float m_new = fmaxf(m_used, mx);
-          const float alpha = ex2_approx((m_used - m_new) * c);
-          m_used = m_new;
-          l *= alpha;
+          if (j > 0) {
+            const float alpha = ex2_approx((m_used - m_new) * c);
+            l *= alpha;
 #pragma unroll 1
-          for (int cc = 0; cc < 4; ++cc) {
-            uint32_t o[32];
-            tmem_ld32(tO + cc * 32, o);
-            tc_wait_ld();
+            for (int cc = 0; cc < 4; ++cc) {
+              uint32_t o[32];
+              tmem_ld32(tO + cc * 32, o);
+              tc_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tO + cc * 32, o);
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st32(tO + cc * 32, o);
+            }
+            tc_wait_st();
           }
-          tc_wait_st();
+          m_used = m_new;
+          neg = -m_used * c;
+          ls2[0] = ls2[1] = 0ull;
+          exp_half<kPolyEvery, false>(s, 0, c, neg, pk, ls2, mxs);
         }
-      }
-      const float neg = -m_used * c;
-      if (tr) ATT_TR(1 + t, 3);
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+        if (tr) ATT_TR(1 + t, 3);
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float xa = fmaf(__uint_as_float(s[hh * 64 + 2 * i]), c, neg);
-          const float xb = fmaf(__uint_as_float(s[hh * 64 + 2 * i + 1]), c, neg);
-          float a = ex2_approx(xa);
-          float b = (kPolyEvery > 0 && (i % (kPolyEvery / 2 > 0 ? kPolyEvery / 2 : 1)) == 0) ? ex2_poly(xb) : ex2_approx(xb);
-          ls[(2 * i) & 3] += a;
-          ls[(2 * i + 1) & 3] += b;
-          pk[i] = pack_bf16x2(a, b);
+        for (int hh = 0; hh < 2; ++hh) {
+          if (hh == 1) exp_half<kPolyEvery, false>(s, 1, c, neg, pk, ls2, mxs);
+          tmem_st32(tS + hh * 32, pk);
+          if (p.p_halves || hh == 1) {
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (!p.p_halves) mbar_arrive(&p_half[2 * t]);
+              mbar_arrive(&p_half[2 * t + hh]);
+            }
+          }
+          if (tr && hh == 0) ATT_TR(1 + t, 4);
         }
-        tmem_st32(tS + hh * 32, pk);
-        if (tr && hh == 0) ATT_TR(1 + t, 4);
+        float s0, s1, s2, s3;
+        unpack2(ls2[0], s0, s1);
+        unpack2(ls2[1], s2, s3);
+        l += (s0 + s1) + (s2 + s3);
       }
-      l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-      tc_wait_st();
       if (tr) ATT_TR(1 + t, 5);
-      tc_fence_before();
-      mbar_arrive(&p_full[t]);
       if (tr) ATT_TR(1 + t, 6);
     }
     // final: PV(n_kv-1) complete
@@ -390,17 +519,18 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     int rc = make_tmap_bf16_sw128(&tmV, vt, 3, dims, str, box);
     if (rc) return rc;
   }
-  // fraction of exponentials evaluated on the FMA pipe: 1/kPolyEvery (0 = none); G3C_ATTN_POLY overrides
-  static int poly = -1;
+  // G3C_ATTN_MODE: softmax variant (see k_attn_fwd); G3C_ATTN_POLY=4: every 4th exponential on the FMA pipe
+  static int poly = -1, mode = 1;
   if (poly < 0) {
     const char* e = getenv("G3C_ATTN_POLY");
-    poly = e ? atoi(e) : 0;
-    if (poly != 0 && poly != 2 && poly != 4 && poly != 8) poly = 4;
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    poly = (e && atoi(e) != 0) ? 4 : 0;
+    e = getenv("G3C_ATTN_MODE");
+    mode = e ? (atoi(e) != 0) : 1;
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<4, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
   }
   AttnParams p;
   p.Lq = Lq;
@@ -414,17 +544,23 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
   p.chunk_flags = gate ? gate->flags : nullptr;
   p.flag_seq = gate ? gate->seq : 0;
   p.first_chunk = gate ? gate->first : 0;
+  static int halves = -1;
+  if (halves < 0) {
+    const char* e = getenv("G3C_ATTN_PHALF");
+    halves = e ? (atoi(e) != 0) : 1;
+  }
+  p.p_halves = halves;
   G3C_REQUIRE(p.first_chunk >= 0 && p.first_chunk < Lk / vt_chunk_len, "attn: first chunk %d out of range", p.first_chunk);
   p.trace = g_attn_trace;
   if (g_attn_trace) {
-    k_attn_fwd<0, true><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+    if (mode) k_attn_fwd<0, true, 1><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+    else k_attn_fwd<0, true, 0><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+  } else if (mode == 0) {
+    k_attn_fwd<0, false, 0><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+  } else if (poly) {
+    k_attn_fwd<4, false, 1><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
   } else {
-    switch (poly) {
-      case 0: k_attn_fwd<0, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-      case 2: k_attn_fwd<2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-      case 8: k_attn_fwd<8, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-      default: k_attn_fwd<4, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-    }
+    k_attn_fwd<0, false, 1><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
   }
   G3C_CUDA(cudaGetLastError());
   return G3C_OK;
