@@ -79,59 +79,14 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
 }
 
-// Packed fp32x2 arithmetic (FFMA2 / FADD2) and the 3-input max (FMNMX3) of sm_100: half the issue slots of the
-// scalar forms for the scale-subtract, the row sums and the row max.
-__device__ __forceinline__ uint64_t pack2(float a, float b) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-  uint64_t r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-  float r;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-  return r;
-}
-
-// Exponentials of the 64 keys of half `hh` of one S row: p = 2^(s*c + neg), packed to bf16 pairs, row sums in two
-// packed accumulators.  kMax additionally folds ALL 128 scores of the row into four max chains (two FMNMX3 per
-// iteration), so the row max of this KV tile is reduced in the shadow of the MUFU-bound exponentials.
-template <int kPolyEvery, bool kMax>
-__device__ __forceinline__ void exp_half(const uint32_t (&s)[128], int hh, float c, float neg, uint32_t (&pk)[32],
-                                         uint64_t (&ls2)[2], float (&mxs)[4]) {
-  const uint64_t c2 = pack2(c, c), n2 = pack2(neg, neg);
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const uint64_t x2 = ffma2(pack2(__uint_as_float(s[hh * 64 + 2 * i]), __uint_as_float(s[hh * 64 + 2 * i + 1])), c2, n2);
-    float xa, xb;
-    unpack2(x2, xa, xb);
-    const float a = ex2_approx(xa);
-    const float b = (kPolyEvery > 0 && (i % (kPolyEvery / 2 > 0 ? kPolyEvery / 2 : 1)) == 0) ? ex2_poly(xb) : ex2_approx(xb);
-    ls2[i & 1] = fadd2(ls2[i & 1], pack2(a, b));
-    pk[i] = pack_bf16x2(a, b);
-    if constexpr (kMax) {
-      mxs[(2 * i) & 3] = fmax3(mxs[(2 * i) & 3], __uint_as_float(s[4 * i]), __uint_as_float(s[4 * i + 1]));
-      mxs[(2 * i + 1) & 3] = fmax3(mxs[(2 * i + 1) & 3], __uint_as_float(s[4 * i + 2]), __uint_as_float(s[4 * i + 3]));
-    }
-  }
-}
-
-// kMode 0: max -> (lazy rescale) -> exponentials, scalar arithmetic.
-// kMode 1: speculative reference max — the exponentials of the first 64 keys are computed against the PREVIOUS
-//          reference max while this tile's max is reduced; only if the max grew past the lazy-rescale threshold
-//          (rare after the first KV tiles) are they recomputed.  Packed fp32x2 arithmetic.
+// kMode 0: exact row max of every KV tile -> lazy rescale -> exponentials.
+// kMode 2: the row max is only reduced for the first KV tile.  Afterwards the exponentials simply keep using the
+//          current reference exponent: fp32 (and bf16 P) carry 8 exponent bits, so a stale reference costs no
+//          precision, only range.  Range is guarded by the row sums that are computed anyway: when a tile's sum
+//          exceeds 2^16 the reference is shifted by that sum's exponent before the next tile (O and the running sum
+//          are scaled by an exact power of two); if a row sum still ends up non-finite — a jump of > 2^100 inside one
+//          tile — the CTA repeats its work once in the exact mode (second pass of the role loops below).
+//          The ~300 clk max reduction leaves the per-tile dependent chain (see the timeline in profiles/).
 template <int kPolyEvery, bool kTrace, int kMode>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
     k_attn_fwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -148,6 +103,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
   uint64_t* s_full = bars + 1 + 2 * ATT_SLOTS;    // [2]
   uint64_t* p_half = bars + 3 + 2 * ATT_SLOTS;    // [tile][key half]: P columns of 64 keys stored
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7 + 2 * ATT_SLOTS);
+  uint32_t* redo_flag = tmem_ptr + 1;  // kMode 2: some row sum left the fp32 range, repeat in the exact mode
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -169,6 +125,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       mbar_init(&p_half[2 * i], 4);      // one elected arrive per softmax warp
       mbar_init(&p_half[2 * i + 1], 4);
     }
+    *redo_flag = 0u;
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(tmem_ptr, 512);
@@ -177,17 +134,25 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // Pipeline state of every role lives outside the pass loop: kMode 2 may run the KV sweep a second time.
+  uint32_t slot = 0, phase = 0;  // KV ring position (TMA warp: producer side, MMA warp: consumer side)
+  uint32_t pph = 0;              // MMA warp: parity of the p_half barriers
+  uint32_t sphase = 0;           // softmax warps: parity of s_full
+  int pass = 0;
+  for (;;) {
+  const bool exact = kMode != 2 || pass == 1;
   if (warp == 8) {
     if (lane == 0) {
       // ===== TMA producer =====
-      mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+      if (pass == 0) {
+        mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
 #pragma unroll
-      for (int t = 0; t < 2; ++t)
+        for (int t = 0; t < 2; ++t)
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-          tma_load_2d(smem_q + t * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmQ, q_full,
-                      head * 128 + h * 64, q0 + t * ATT_TILE);
-      uint32_t slot = 0, phase = 0;
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d(smem_q + t * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmQ, q_full,
+                        head * 128 + h * 64, q0 + t * ATT_TILE);
+      }
       const int tiles_per_chunk = p.vt_chunk_len / ATT_TILE;
       const int n_chunks = p.Lk / p.vt_chunk_len;
       for (int j = 0; j < n_kv; ++j) {
@@ -236,7 +201,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       constexpr uint32_t idesc = make_idesc_bf16(128, 128);
       const uint32_t tS[2] = {tmem_base, tmem_base + 128};
       const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
-      uint32_t slot = 0, phase = 0;
       auto advance = [&]() { if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; } };
       auto mma_s = [&](int t, uint32_t kslot) {
         // S_t = Q_t K^T : 8 k-steps over the head dimension
@@ -258,7 +222,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           umma_ts(tO[t], tS[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
         }
       };
-      mbar_wait(q_full, 0);
+      if (pass == 0) mbar_wait(q_full, 0);
       mbar_wait(&kv_full[slot], phase);
       tc_fence_after();
       uint32_t kslot = slot;
@@ -276,11 +240,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         // ---- tile A
         ATT_TR(0, 0);
         // the P·V MMAs of the first 64 keys start while the softmax still exponentiates the second 64
-        mbar_wait(&p_half[0], j & 1);
+        mbar_wait(&p_half[0], pph);
         ATT_TR(0, 1);
         tc_fence_after();
         mma_pv(0, vslot, j == 0, 0);
-        mbar_wait(&p_half[1], j & 1);
+        mbar_wait(&p_half[1], pph);
         tc_fence_after();
         mma_pv(0, vslot, j == 0, 1);
         if (more) {
@@ -293,11 +257,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         umma_commit(&s_full[0]);
         ATT_TR(0, 2);
         // ---- tile B
-        mbar_wait(&p_half[2], j & 1);
+        mbar_wait(&p_half[2], pph);
         ATT_TR(0, 3);
         tc_fence_after();
         mma_pv(1, vslot, j == 0, 0);
-        mbar_wait(&p_half[3], j & 1);
+        mbar_wait(&p_half[3], pph);
         tc_fence_after();
         mma_pv(1, vslot, j == 0, 1);
         umma_commit(&kv_empty[vslot]);
@@ -308,6 +272,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         } else {
           umma_commit(&s_full[1]);
         }
+        pph ^= 1;
         ATT_TR(0, 4);
       }
     }
@@ -318,10 +283,24 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     const uint32_t tS = tmem_base + lane_base + t * 128;
     const uint32_t tO = tmem_base + lane_base + 256 + t * 128;
     const float c = p.scale_log2;
-    float m_used = kMode == 0 ? 0.0f : -INFINITY;  // reference max (raw score units) the stored exponentials are relative to
-    float l = 0.0f;       // running row sum (relative to m_used)
-    uint32_t sphase = 0;
+    float ref = 0.0f;   // reference exponent (log2 units): the stored exponentials are 2^(s*c - ref)
+    float l = 0.0f;     // running row sum (relative to ref)
+    float pend = 0.0f;  // kMode 2: exponent shift to apply to ref / O / l before the next tile (0 = none)
     const bool tr = kTrace && (warp & 3) == 0 && lane == 0;
+    auto rescale = [&](float alpha) {
+      // s_full(j) was committed after PV(j-1): O already holds every earlier contribution.
+      l *= alpha;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t o[32];
+        tmem_ld32(tO + cc * 32, o);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st32(tO + cc * 32, o);
+      }
+      tc_wait_st();
+    };
     for (int j = 0; j < n_kv; ++j) {
       if (tr) ATT_TR(1 + t, 0);
       mbar_wait(&s_full[t], sphase);
@@ -333,127 +312,72 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       for (int cc = 0; cc < 4; ++cc) tmem_ld32(tS + cc * 32, s + cc * 32);
       tc_wait_ld();
       if (tr) ATT_TR(1 + t, 2);
-      if constexpr (kMode == 0) {
-      // 8 independent max chains (a single dependent FMNMX chain costs ~6 clk per link: 400 clk per tile
-        // in the round-1 profile)
+      if (exact || j == 0) {
+        // 8 independent max chains (a single dependent FMNMX chain costs ~6 clk per link)
         float mxs[8];
-  #pragma unroll
+#pragma unroll
         for (int i = 0; i < 8; ++i) mxs[i] = __uint_as_float(s[i]);
-  #pragma unroll
+#pragma unroll
         for (int i = 8; i < 128; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], __uint_as_float(s[i]));
-        const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
-                               fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+        const float mxl = c * fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                                    fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
         if (j == 0) {
-          m_used = mx;
-        } else {
-          const bool grow = (mx - m_used) * c > 8.0f;
-          if (__any_sync(0xffffffffu, grow)) {
-            // s_full(j) was committed after PV(j-1): O already holds every earlier contribution.
-            const float m_new = fmaxf(m_used, mx);
-            const float alpha = ex2_approx((m_used - m_new) * c);
-            m_used = m_new;
-            l *= alpha;
-  #pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
-              uint32_t o[32];
-              tmem_ld32(tO + cc * 32, o);
-              tc_wait_ld();
-  #pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st32(tO + cc * 32, o);
-            }
-            tc_wait_st();
-          }
+          ref = mxl;
+        } else if (__any_sync(0xffffffffu, mxl - ref > 8.0f)) {  // lazy: only when the max grew by > 2^8
+          const float nref = fmaxf(ref, mxl);
+          rescale(ex2_approx(ref - nref));
+          ref = nref;
         }
-        const float neg = -m_used * c;
-        if (tr) ATT_TR(1 + t, 3);
-        float ls[4] = {0.f, 0.f, 0.f, 0.f};
-  #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t pk[32];
-  #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float xa = fmaf(__uint_as_float(s[hh * 64 + 2 * i]), c, neg);
-            const float xb = fmaf(__uint_as_float(s[hh * 64 + 2 * i + 1]), c, neg);
-            float a = ex2_approx(xa);
-            float b = (kPolyEvery > 0 && (i % (kPolyEvery / 2 > 0 ? kPolyEvery / 2 : 1)) == 0) ? ex2_poly(xb) : ex2_approx(xb);
-            ls[(2 * i) & 3] += a;
-            ls[(2 * i + 1) & 3] += b;
-            pk[i] = pack_bf16x2(a, b);
-          }
-          tmem_st32(tS + hh * 32, pk);
-          if (p.p_halves || hh == 1) {
-            tc_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (!p.p_halves) mbar_arrive(&p_half[2 * t]);
-              mbar_arrive(&p_half[2 * t + hh]);
-            }
-          }
-          if (tr && hh == 0) ATT_TR(1 + t, 4);
-        }
-        l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-      } else {
-        // fp32 keeps the full exponent range in P (bf16) and in O / l, so the rescale threshold only guards
-        // against overflow: 2^24 here (the stored exponentials are <= 2^24, row sums <= 2^24 * Lk).
-        constexpr float kGrow = 24.0f;
+      } else if (__any_sync(0xffffffffu, pend != 0.0f)) {
+        rescale(__int_as_float((127 - (int)pend) << 23));  // exact power of two
+        ref += pend;
+        pend = 0.0f;
+      }
+      const float neg = -ref;
+      if (tr) ATT_TR(1 + t, 3);
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
         uint32_t pk[32];
-        uint64_t ls2[2] = {0ull, 0ull};
-        float mxs[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        float neg = -m_used * c;  // j == 0: m_used = -inf, every row takes the slow path below
-        exp_half<kPolyEvery, true>(s, 0, c, neg, pk, ls2, mxs);
-        const float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
-        const bool grow = !((mx - m_used) * c <= kGrow);
-        if (__any_sync(0xffffffffu, grow)) {
-          // s_full(j) was committed after PV(j-1): O already holds every earlier contribution.
-          const float m_new = fmaxf(m_used, mx);
-          if (j > 0) {
-            const float alpha = ex2_approx((m_used - m_new) * c);
-            l *= alpha;
-#pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
-              uint32_t o[32];
-              tmem_ld32(tO + cc * 32, o);
-              tc_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st32(tO + cc * 32, o);
-            }
-            tc_wait_st();
-          }
-          m_used = m_new;
-          neg = -m_used * c;
-          ls2[0] = ls2[1] = 0ull;
-          exp_half<kPolyEvery, false>(s, 0, c, neg, pk, ls2, mxs);
+        for (int i = 0; i < 32; ++i) {
+          const float xa = fmaf(__uint_as_float(s[hh * 64 + 2 * i]), c, neg);
+          const float xb = fmaf(__uint_as_float(s[hh * 64 + 2 * i + 1]), c, neg);
+          float a = ex2_approx(xa);
+          float b = (kPolyEvery > 0 && (i % (kPolyEvery / 2 > 0 ? kPolyEvery / 2 : 1)) == 0) ? ex2_poly(xb) : ex2_approx(xb);
+          ls[(2 * i) & 3] += a;
+          ls[(2 * i + 1) & 3] += b;
+          pk[i] = pack_bf16x2(a, b);
         }
-        if (tr) ATT_TR(1 + t, 3);
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          if (hh == 1) exp_half<kPolyEvery, false>(s, 1, c, neg, pk, ls2, mxs);
-          tmem_st32(tS + hh * 32, pk);
-          if (p.p_halves || hh == 1) {
-            tc_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (!p.p_halves) mbar_arrive(&p_half[2 * t]);
-              mbar_arrive(&p_half[2 * t + hh]);
-            }
+        tmem_st32(tS + hh * 32, pk);
+        if (p.p_halves || hh == 1) {
+          tc_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (!p.p_halves) mbar_arrive(&p_half[2 * t]);
+            mbar_arrive(&p_half[2 * t + hh]);
           }
-          if (tr && hh == 0) ATT_TR(1 + t, 4);
         }
-        float s0, s1, s2, s3;
-        unpack2(ls2[0], s0, s1);
-        unpack2(ls2[1], s2, s3);
-        l += (s0 + s1) + (s2 + s3);
+        if (tr && hh == 0) ATT_TR(1 + t, 4);
+      }
+      const float tsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
+      l += tsum;
+      if (!exact) {
+        // inf: exponent field 255 -> shift 100, l is non-finite by then and the CTA takes the exact second pass
+        const int e = ((__float_as_int(tsum) >> 23) & 0xff) - 127;
+        pend = tsum > 65536.0f ? (float)(e < 100 ? e : 100) : 0.0f;
       }
       if (tr) ATT_TR(1 + t, 5);
       if (tr) ATT_TR(1 + t, 6);
     }
     // final: PV(n_kv-1) complete
     mbar_wait(&s_full[t], sphase);
+    sphase ^= 1;
     tc_fence_after();
+    if constexpr (kMode == 2) {
+      if (pass == 0 && !(l < 1e30f)) *reinterpret_cast<volatile uint32_t*>(redo_flag) = 1u;
+    }
     const int row = q0 + t * ATT_TILE + (warp & 3) * 32 + lane;
     const float inv = 1.0f / l;
     __nv_bfloat16* optr = p.O + (size_t)row * p.ldo + head * 128;
@@ -473,6 +397,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           reinterpret_cast<uint4*>(optr + cc * 32)[i] = q;
         }
       }
+    }
+  }
+    if constexpr (kMode != 2) {
+      break;
+    } else {
+      // did any row of this CTA leave the fp32 range?  (never for RMS-normalised q/k; the generic kernel must cope)
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      if (pass == 1 || *reinterpret_cast<volatile uint32_t*>(redo_flag) == 0u) break;
+      pass = 1;
     }
   }
 
@@ -519,18 +454,19 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     int rc = make_tmap_bf16_sw128(&tmV, vt, 3, dims, str, box);
     if (rc) return rc;
   }
-  // G3C_ATTN_MODE: softmax variant (see k_attn_fwd); G3C_ATTN_POLY=4: every 4th exponential on the FMA pipe
-  static int poly = -1, mode = 1;
+  // G3C_ATTN_MODE: softmax variant (see k_attn_fwd), 2 = sum-guarded reference (default), 0 = exact max per tile;
+  // G3C_ATTN_POLY=4: every 4th exponential on the FMA pipe (measured slower, kept for A/B runs)
+  static int poly = -1, mode = 2;
   if (poly < 0) {
     const char* e = getenv("G3C_ATTN_POLY");
     poly = (e && atoi(e) != 0) ? 4 : 0;
     e = getenv("G3C_ATTN_MODE");
-    mode = e ? (atoi(e) != 0) : 1;
+    mode = e ? (atoi(e) != 0 ? 2 : 0) : 2;
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<4, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<4, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
   }
   AttnParams p;
   p.Lq = Lq;
@@ -553,14 +489,14 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
   G3C_REQUIRE(p.first_chunk >= 0 && p.first_chunk < Lk / vt_chunk_len, "attn: first chunk %d out of range", p.first_chunk);
   p.trace = g_attn_trace;
   if (g_attn_trace) {
-    if (mode) k_attn_fwd<0, true, 1><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+    if (mode) k_attn_fwd<0, true, 2><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
     else k_attn_fwd<0, true, 0><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
   } else if (mode == 0) {
     k_attn_fwd<0, false, 0><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
   } else if (poly) {
-    k_attn_fwd<4, false, 1><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+    k_attn_fwd<4, false, 2><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
   } else {
-    k_attn_fwd<0, false, 1><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+    k_attn_fwd<0, false, 2><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
   }
   G3C_CUDA(cudaGetLastError());
   return G3C_OK;

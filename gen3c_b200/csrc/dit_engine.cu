@@ -120,6 +120,11 @@ struct g3c_dit {
   void* peer_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool peers_open = false;
   uint32_t kv_seq = 0;
+  // pinned ring of sequence numbers: the copy engine writes flags[rank] = seq on every peer by copying 4 bytes from
+  // here after the K / V^T copies (no kernel on the side stream: a flag kernel queued behind a grid whose CTAs spin
+  // on exactly that flag would never be dispatched)
+  uint32_t* seq_ring = nullptr;
+  static constexpr uint32_t kSeqRing = 8192;
   // workspace
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -373,9 +378,10 @@ static int forward(g3c_dit* h, const void* x_in, const void* cond_mask, const vo
             G3C_CUDA(cudaMemcpyAsync(pk.ptr[i2], kl, slice, cudaMemcpyDeviceToDevice, h->comm_stream));
             G3C_CUDA(cudaMemcpyAsync(pv.ptr[i2], vl, slice, cudaMemcpyDeviceToDevice, h->comm_stream));
           }
-          k_cp_signal<<<1, 32, 0, h->comm_stream>>>(pf, seq);
-          G3C_CUDA(cudaGetLastError());
-          n += 2 * pk.n + 1;
+          uint32_t* slot = h->seq_ring + (seq % g3c_dit::kSeqRing);
+          *slot = seq;  // read by the copy engine when the copies above have completed
+          for (int i2 = 0; i2 < pf.n; ++i2)
+            G3C_CUDA(cudaMemcpyAsync(pf.ptr[i2], slot, 4, cudaMemcpyHostToDevice, h->comm_stream));
         }
         K(CAT_GEMM, gemm_bf16(h->xn, s.wq, h->q, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
         K(CAT_ELTWISE, rmsnorm_rope(h->q, D, L, heads, s.gq, h->rope, 1e-6f, st));
@@ -483,6 +489,7 @@ int g3c_dit_destroy(g3c_dit_t* h) {
   if (h->gammas) cudaFree(h->gammas);
   if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
+  if (h->seq_ring) cudaFreeHost(h->seq_ring);
   if (h->ev_kv) cudaEventDestroy(h->ev_kv);
   if (h->ev_gathered) cudaEventDestroy(h->ev_gathered);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -534,7 +541,12 @@ int g3c_dit_enable_cp(g3c_dit_t* h, const void* nccl_unique_id, int cp_rank, int
     memcpy(&id, nccl_unique_id, 128);
     G3C_NCCL(nccl().CommInitRank(&h->comm, cp_size, id, cp_rank));
   }
-  if (!h->comm_stream) G3C_CUDA(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+  if (!h->comm_stream) {
+    int lo = 0, hi = 0;
+    G3C_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    G3C_CUDA(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, hi));
+  }
+  if (!h->seq_ring) G3C_CUDA(cudaHostAlloc(&h->seq_ring, g3c_dit::kSeqRing * sizeof(uint32_t), cudaHostAllocPortable));
   if (!h->ev_kv) G3C_CUDA(cudaEventCreateWithFlags(&h->ev_kv, cudaEventDisableTiming));
   if (!h->ev_gathered) G3C_CUDA(cudaEventCreateWithFlags(&h->ev_gathered, cudaEventDisableTiming));
   h->cp_rank = cp_rank;

@@ -526,7 +526,15 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int ld
   }
   // block_n 512 = CTA-pair kernel (256 x 256 tile over two SMs); chosen automatically for large, aligned problems
   // (G3C_GEMM_2CTA=0 disables it)
-  if (bn == 0 && pair_default && N % 256 == 0 && M >= 1024 && K >= 256) bn = 512;
+  if (bn == 0 && pair_default && N % 256 == 0 && M >= 1024 && K >= 256) {
+    // wave quantisation: a pair tile is 256 x 256 on two SMs, a single tile 128 x 256 on one, i.e. the same work per
+    // SM and wave; the pair kernel is ~6 % faster per wave (half the B traffic) unless it needs an extra, mostly
+    // empty wave (e.g. M = 7 040 = 27.5 pair rows at cp = 8: 7 waves against 6).
+    const int sms = sm_count();
+    const long long tiles_p = (long long)((M + 255) / 256) * (N / 256), tiles_s = (long long)((M + 127) / 128) * (N / 256);
+    const long long waves_p = (tiles_p + sms / 2 - 1) / (sms / 2), waves_s = (tiles_s + sms - 1) / sms;
+    bn = (100 * waves_p <= 106 * waves_s) ? 512 : 256;
+  }
   if (bn == 0) bn = (N >= 256 && N % 256 == 0) ? 256 : (N > 64 ? 128 : 64);
   G3C_REQUIRE(bn == 64 || bn == 128 || bn == 256 || bn == 512, "gemm: block_n %d unsupported", bn);
   const bool pair = bn == 512;

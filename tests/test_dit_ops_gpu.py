@@ -109,6 +109,25 @@ def test_attention_peaked_softmax():
     assert rel(o, ref) < 8e-3, rel(o, ref)
 
 
+@pytest.mark.parametrize("jump", [4.0, 9.5])
+def test_attention_score_jump(jump):
+    """A block of keys far above everything before it, inside one KV tile.  jump=4: the tile's row sums reach ~2^65,
+    which the default softmax (reference exponent guarded by the row sums) absorbs by shifting the reference before
+    the next tile.  jump=9.5: 2^155 overflows fp32 inside that tile, so the CTA must repeat its sweep in the exact
+    (max-per-tile) mode.  Both must match the fp32 reference, and the exact mode is the same kernel with
+    G3C_ATTN_MODE=0."""
+    from gen3c_b200 import ops
+
+    heads, Lq, Lk = 2, 384, 1024
+    q, k, v = bf(Lq, heads * 128, seed=20, s=0.5), bf(Lk, heads * 128, seed=21, s=0.5), bf(Lk, heads * 128, seed=22)
+    q[:, :128] = 1.0  # head 0: constant queries; head 1 stays random
+    k[300:340, :128] = jump  # scores 128 * jump / sqrt(128) = 11.3 * jump nats above the rest, in KV tile 2
+    ref = sdpa_ref(q, k, v, heads)
+    o = ops.attention(q, k, v.T.contiguous(), heads)
+    assert torch.isfinite(o.float()).all()
+    assert rel(o, ref) < 5e-3, rel(o, ref)
+
+
 def test_ln_modulate():
     from gen3c_b200 import ops
 
