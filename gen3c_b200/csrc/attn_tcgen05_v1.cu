@@ -27,6 +27,7 @@
 // exponentials of the first half, which speculatively use the previous reference max; O / row sum are
 // only rescaled (and that half recomputed) when the max grew past the lazy threshold — rare after
 // the first KV tiles; fp32x2 packed FFMA/FADD and 3-input max halve the non-MUFU issue slots.
+#include <cmath>
 #include <cstdlib>
 
 #include "kernels.h"
@@ -50,6 +51,7 @@ struct AttnParams {
   const uint32_t* chunk_flags;  // context-parallel gate (or NULL): chunk c readable once chunk_flags[c] >= flag_seq
   uint32_t flag_seq;
   int first_chunk;
+  int unit_scale;             // 1: scale_log2 == 1 (the caller folded softmax scale * log2 e into Q): S is in log2 units
   int p_halves;               // 1: P is released to the MMA warp per 64-key half, 0: per 128-key tile
   unsigned long long* trace;  // kTrace only: [3 roles][64 steps][8 slots] clock64 stamps of CTA (0,0)
 };
@@ -65,6 +67,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
   return y;
+}
+
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {  // FADD2: two fp32 adds in one instruction
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
 }
 
 // 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, rel. err 7.5e-5, far below the bf16
@@ -87,7 +103,9 @@ __device__ __forceinline__ float ex2_poly(float x) {
 //          are scaled by an exact power of two); if a row sum still ends up non-finite — a jump of > 2^100 inside one
 //          tile — the CTA repeats its work once in the exact mode (second pass of the role loops below).
 //          The ~300 clk max reduction leaves the per-tile dependent chain (see the timeline in profiles/).
-template <int kPolyEvery, bool kTrace, int kMode>
+// kCluster: the CTAs of two neighbouring query blocks of one head form a cluster; each TMA-loads HALF of every K / V
+//           tile and multicasts it into both CTAs' rings, so every K / V byte leaves L2 once per 512 query rows.
+template <int kPolyEvery, int kTrace, int kMode, bool kCluster>  // kTrace 1: stamps in every role, 2: MMA warp only
 __global__ void __launch_bounds__(ATT_THREADS, 1)
     k_attn_fwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -118,7 +136,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     mbar_init(q_full, 1);
     for (int i = 0; i < ATT_SLOTS; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], kCluster ? 2 : 1);  // cluster: the slot is rewritten in both CTAs, both consumers release it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
@@ -131,8 +149,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
   if (warp == 9) tmem_alloc(tmem_ptr, 512);
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCluster) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t crank = kCluster ? cluster_ctarank() : 0u;
 
   // Pipeline state of every role lives outside the pass loop: kMode 2 may run the KV sweep a second time.
   uint32_t slot = 0, phase = 0;  // KV ring position (TMA warp: producer side, MMA warp: consumer side)
@@ -179,19 +199,29 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         // K_j
         mbar_wait(&kv_empty[slot], phase ^ 1);
         mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
+        if constexpr (kCluster) {
+          tma_load_2d_mc(smem_kv + slot * ATT_TILE_BYTES + crank * ATT_HALF_BYTES, &tmK, &kv_full[slot],
+                         head * 128 + crank * 64, kv0, 3);
+        } else {
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-          tma_load_2d(smem_kv + slot * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmK, &kv_full[slot],
-                      head * 128 + h * 64, kv0);
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d(smem_kv + slot * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmK, &kv_full[slot],
+                        head * 128 + h * 64, kv0);
+        }
         if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; }
         // V_j  (transposed: rows = head dim, columns = keys)
         mbar_wait(&kv_empty[slot], phase ^ 1);
         mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
         const int koff = within * ATT_TILE;
+        if constexpr (kCluster) {
+          tma_load_3d_mc(smem_kv + slot * ATT_TILE_BYTES + crank * ATT_HALF_BYTES, &tmV, &kv_full[slot],
+                         koff + crank * 64, head * 128, chunk, 3);
+        } else {
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-          tma_load_3d(smem_kv + slot * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmV, &kv_full[slot],
-                      koff + h * 64, head * 128, chunk);
+          for (int h = 0; h < 2; ++h)
+            tma_load_3d(smem_kv + slot * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmV, &kv_full[slot],
+                        koff + h * 64, head * 128, chunk);
+        }
         if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; }
       }
     }
@@ -202,6 +232,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       const uint32_t tS[2] = {tmem_base, tmem_base + 128};
       const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
       auto advance = [&]() { if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; } };
+      auto release_slot = [&](uint32_t sl) {
+        if constexpr (kCluster) umma_commit_mc(&kv_empty[sl], 3);
+        else umma_commit(&kv_empty[sl]);
+      };
       auto mma_s = [&](int t, uint32_t kslot) {
         // S_t = Q_t K^T : 8 k-steps over the head dimension
 #pragma unroll
@@ -231,7 +265,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       umma_commit(&s_full[0]);
       mma_s(1, kslot);
       umma_commit(&s_full[1]);
-      umma_commit(&kv_empty[kslot]);
+      release_slot(kslot);
       for (int j = 0; j < n_kv; ++j) {
         const bool more = j + 1 < n_kv;
         mbar_wait(&kv_full[slot], phase);  // V_j
@@ -264,11 +298,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         mbar_wait(&p_half[3], pph);
         tc_fence_after();
         mma_pv(1, vslot, j == 0, 1);
-        umma_commit(&kv_empty[vslot]);
+        release_slot(vslot);
         if (more) {
           mma_s(1, kslot);
           umma_commit(&s_full[1]);
-          umma_commit(&kv_empty[kslot]);
+          release_slot(kslot);
         } else {
           umma_commit(&s_full[1]);
         }
@@ -285,8 +319,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     const float c = p.scale_log2;
     float ref = 0.0f;   // reference exponent (log2 units): the stored exponentials are 2^(s*c - ref)
     float l = 0.0f;     // running row sum (relative to ref)
+    bool ovf = false;   // kMode 2: the running row sum left the safe range at some tile
+    bool plain = false; // kMode 2: ref == 0 in every row of this warp and S is in log2 units
     float pend = 0.0f;  // kMode 2: exponent shift to apply to ref / O / l before the next tile (0 = none)
-    const bool tr = kTrace && (warp & 3) == 0 && lane == 0;
+    const bool tr = kTrace == 1 && (warp & 3) == 0 && lane == 0;
     auto rescale = [&](float alpha) {
       // s_full(j) was committed after PV(j-1): O already holds every earlier contribution.
       l *= alpha;
@@ -301,82 +337,160 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       }
       tc_wait_st();
     };
-    for (int j = 0; j < n_kv; ++j) {
+    // exponentials of 64 keys (S values in sv) -> bf16 pairs in pk, partial row sums in ls
+    auto exp64 = [&](const uint32_t* sv, float neg, uint32_t* pk, float* ls) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float xa = fmaf(__uint_as_float(sv[2 * i]), c, neg);
+        const float xb = fmaf(__uint_as_float(sv[2 * i + 1]), c, neg);
+        const float a = ex2_approx(xa);
+        const float b = (kPolyEvery > 0 && (i % (kPolyEvery / 2 > 0 ? kPolyEvery / 2 : 1)) == 0) ? ex2_poly(xb) : ex2_approx(xb);
+        ls[(2 * i) & 3] += a;
+        ls[(2 * i + 1) & 3] += b;
+        pk[i] = pack_bf16x2(a, b);
+      }
+    };
+    // P columns of half hh are in TMEM: make them visible to the tensor pipe and tell the MMA warp
+    auto release_half = [&](int hh) {
+      if (p.p_halves || hh == 1) {
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (!p.p_halves) mbar_arrive(&p_half[2 * t]);
+          mbar_arrive(&p_half[2 * t + hh]);
+        }
+      }
+    };
+    auto wait_s = [&](int j) {
       if (tr) ATT_TR(1 + t, 0);
       mbar_wait(&s_full[t], sphase);
       if (tr) ATT_TR(1 + t, 1);
       sphase ^= 1;
       tc_fence_after();
+    };
+    // exact tile: whole S row in registers, row max, lazy rescale, exponentials
+    auto tile_exact = [&](int j) {
+      wait_s(j);
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t s[128];
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) tmem_ld32(tS + cc * 32, s + cc * 32);
       tc_wait_ld();
       if (tr) ATT_TR(1 + t, 2);
-      if (exact || j == 0) {
-        // 8 independent max chains (a single dependent FMNMX chain costs ~6 clk per link)
-        float mxs[8];
+      // 8 independent max chains (a single dependent FMNMX chain costs ~6 clk per link)
+      float mxs[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mxs[i] = __uint_as_float(s[i]);
+      for (int i = 0; i < 8; ++i) mxs[i] = __uint_as_float(s[i]);
 #pragma unroll
-        for (int i = 8; i < 128; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], __uint_as_float(s[i]));
-        const float mxl = c * fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
-                                    fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
-        if (j == 0) {
-          ref = mxl;
-        } else if (__any_sync(0xffffffffu, mxl - ref > 8.0f)) {  // lazy: only when the max grew by > 2^8
-          const float nref = fmaxf(ref, mxl);
-          rescale(ex2_approx(ref - nref));
-          ref = nref;
-        }
-      } else if (__any_sync(0xffffffffu, pend != 0.0f)) {
-        rescale(__int_as_float((127 - (int)pend) << 23));  // exact power of two
-        ref += pend;
-        pend = 0.0f;
+      for (int i = 8; i < 128; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], __uint_as_float(s[i]));
+      const float mxl = c * fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                                  fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+      if (j == 0) {
+        // kMode 2 with S already in log2 units: if every first-tile row max of this warp is within 2^+-40 the
+        // reference stays 0 and the fast tiles need no subtraction at all (p = 2^s)
+        plain = !exact && p.unit_scale && __all_sync(0xffffffffu, fabsf(mxl) <= 40.0f);
+        ref = plain ? 0.0f : mxl;
+      } else if (__any_sync(0xffffffffu, mxl - ref > 8.0f)) {  // lazy: only when the max grew by > 2^8
+        const float nref = fmaxf(ref, mxl);
+        rescale(ex2_approx(ref - nref));
+        ref = nref;
       }
-      const float neg = -ref;
       if (tr) ATT_TR(1 + t, 3);
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float xa = fmaf(__uint_as_float(s[hh * 64 + 2 * i]), c, neg);
-          const float xb = fmaf(__uint_as_float(s[hh * 64 + 2 * i + 1]), c, neg);
-          float a = ex2_approx(xa);
-          float b = (kPolyEvery > 0 && (i % (kPolyEvery / 2 > 0 ? kPolyEvery / 2 : 1)) == 0) ? ex2_poly(xb) : ex2_approx(xb);
-          ls[(2 * i) & 3] += a;
-          ls[(2 * i + 1) & 3] += b;
-          pk[i] = pack_bf16x2(a, b);
-        }
+        exp64(s + hh * 64, -ref, pk, ls);
         tmem_st32(tS + hh * 32, pk);
-        if (p.p_halves || hh == 1) {
-          tc_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (!p.p_halves) mbar_arrive(&p_half[2 * t]);
-            mbar_arrive(&p_half[2 * t + hh]);
-          }
-        }
+        release_half(hh);
         if (tr && hh == 0) ATT_TR(1 + t, 4);
       }
-      const float tsum = (ls[0] + ls[1]) + (ls[2] + ls[3]);
-      l += tsum;
-      if (!exact) {
-        // inf: exponent field 255 -> shift 100, l is non-finite by then and the CTA takes the exact second pass
-        const int e = ((__float_as_int(tsum) >> 23) & 0xff) - 127;
-        pend = tsum > 65536.0f ? (float)(e < 100 ? e : 100) : 0.0f;
-      }
+      l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
       if (tr) ATT_TR(1 + t, 5);
       if (tr) ATT_TR(1 + t, 6);
+    };
+    // fast tile (kMode 2, j > 0): no row max; S is read 64 columns at a time so that only half a row is live.
+    // Row sums exceeding kBig shift the reference before the next tile (see the kMode comment).
+    auto fast_tail = [&](float tsum, int j) {
+      l += tsum;
+      // sticky: O <= l * max|v|, so a running sum that stays below 2^90 keeps O finite as well; a transient excursion
+      // (later scaled away by a shift) would otherwise leave inf in O behind a harmless-looking final l
+      ovf |= !(l < 1e27f);
+      // inf: exponent field 255 -> shift 100, l is non-finite by then and the CTA takes the exact second pass
+      const int e = ((__float_as_int(tsum) >> 23) & 0xff) - 127;
+      pend = tsum > 1.0995116e12f /* 2^40 */ ? (float)(e < 100 ? e : 100) : 0.0f;
+      if (tr) ATT_TR(1 + t, 5);
+      if (tr) ATT_TR(1 + t, 6);
+    };
+    auto tile_fast = [&](int j) {
+      wait_s(j);
+      if (__any_sync(0xffffffffu, pend != 0.0f)) {
+        rescale(__int_as_float((127 - (int)pend) << 23));  // exact power of two
+        ref += pend;
+        pend = 0.0f;
+        plain = false;
+      }
+      uint32_t s[64], pk[32];
+      tmem_ld32(tS, s);
+      tmem_ld32(tS + 32, s + 32);
+      tc_wait_ld();
+      if (tr) ATT_TR(1 + t, 2);
+      if (tr) ATT_TR(1 + t, 3);
+      if (plain) {
+        // p = 2^s: one MUFU per element, one FADD2 and one F2FP per pair
+        uint64_t ls2[2] = {0ull, 0ull};
+        auto exp64p = [&]() {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float a = ex2_approx(__uint_as_float(s[2 * i])), b = ex2_approx(__uint_as_float(s[2 * i + 1]));
+            ls2[i & 1] = fadd2(ls2[i & 1], pack2(a, b));
+            pk[i] = pack_bf16x2(a, b);
+          }
+        };
+        exp64p();
+        tmem_st32(tS, pk);
+        tmem_ld32(tS + 64, s);  // second half of the row arrives under the release of the first P half
+        tmem_ld32(tS + 96, s + 32);
+        release_half(0);
+        if (tr) ATT_TR(1 + t, 4);
+        tc_wait_ld();
+        exp64p();
+        tmem_st32(tS + 32, pk);
+        release_half(1);
+        float s0, s1, s2, s3;
+        unpack2(ls2[0], s0, s1);
+        unpack2(ls2[1], s2, s3);
+        fast_tail((s0 + s1) + (s2 + s3), j);
+      } else {
+        const float neg = -ref;
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+        exp64(s, neg, pk, ls);
+        tmem_st32(tS, pk);
+        tmem_ld32(tS + 64, s);
+        tmem_ld32(tS + 96, s + 32);
+        release_half(0);
+        if (tr) ATT_TR(1 + t, 4);
+        tc_wait_ld();
+        exp64(s, neg, pk, ls);
+        tmem_st32(tS + 32, pk);
+        release_half(1);
+        fast_tail((ls[0] + ls[1]) + (ls[2] + ls[3]), j);
+      }
+    };
+    if (exact) {
+#pragma unroll 1
+      for (int j = 0; j < n_kv; ++j) tile_exact(j);
+    } else {
+      tile_exact(0);
+#pragma unroll 1
+      for (int j = 1; j < n_kv; ++j) tile_fast(j);
     }
     // final: PV(n_kv-1) complete
     mbar_wait(&s_full[t], sphase);
     sphase ^= 1;
     tc_fence_after();
     if constexpr (kMode == 2) {
-      if (pass == 0 && !(l < 1e30f)) *reinterpret_cast<volatile uint32_t*>(redo_flag) = 1u;
+      if (pass == 0 && (ovf || !(l < 1e27f))) *reinterpret_cast<volatile uint32_t*>(redo_flag) = 1u;
     }
     const int row = q0 + t * ATT_TILE + (warp & 3) * 32 + lane;
     const float inv = 1.0f / l;
@@ -405,6 +519,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       // did any row of this CTA leave the fp32 range?  (never for RMS-normalised q/k; the generic kernel must cope)
       tc_fence_before();
       __syncthreads();
+      if constexpr (kCluster) {
+        // both CTAs of a cluster share the K / V ring protocol: they repeat the sweep together or not at all
+        if (threadIdx.x == 0 && pass == 0 && *reinterpret_cast<volatile uint32_t*>(redo_flag) != 0u)
+          st_shared_cluster_u32(redo_flag, crank ^ 1u, 1u);
+        cluster_sync_all();
+      }
       tc_fence_after();
       if (pass == 1 || *reinterpret_cast<volatile uint32_t*>(redo_flag) == 0u) break;
       pass = 1;
@@ -413,6 +533,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCluster) cluster_sync_all();  // no arrive / multicast may target a CTA that has already exited
   if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -456,17 +577,21 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
   }
   // G3C_ATTN_MODE: softmax variant (see k_attn_fwd), 2 = sum-guarded reference (default), 0 = exact max per tile;
   // G3C_ATTN_POLY=4: every 4th exponential on the FMA pipe (measured slower, kept for A/B runs)
-  static int poly = -1, mode = 2;
+  static int poly = -1, mode = 2, cluster = 0;
   if (poly < 0) {
     const char* e = getenv("G3C_ATTN_POLY");
     poly = (e && atoi(e) != 0) ? 4 : 0;
     e = getenv("G3C_ATTN_MODE");
     mode = e ? (atoi(e) != 0 ? 2 : 0) : 2;
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<4, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 0, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<4, 0, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 1, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 1, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    e = getenv("G3C_ATTN_CLUSTER");
+    cluster = e ? atoi(e) != 0 : 0;
   }
   AttnParams p;
   p.Lq = Lq;
@@ -476,6 +601,8 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
   p.vt_chunk_len = vt_chunk_len;
   p.O = reinterpret_cast<__nv_bfloat16*>(o);
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.unit_scale = fabsf(p.scale_log2 - 1.0f) < 1e-6f;  // scale = ln 2: the caller already folded scale * log2(e) into Q
+  if (p.unit_scale) p.scale_log2 = 1.0f;
   dim3 grid((Lq + 2 * ATT_TILE - 1) / (2 * ATT_TILE), heads);
   p.chunk_flags = gate ? gate->flags : nullptr;
   p.flag_seq = gate ? gate->seq : 0;
@@ -489,14 +616,32 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
   G3C_REQUIRE(p.first_chunk >= 0 && p.first_chunk < Lk / vt_chunk_len, "attn: first chunk %d out of range", p.first_chunk);
   p.trace = g_attn_trace;
   if (g_attn_trace) {
-    if (mode) k_attn_fwd<0, true, 2><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
-    else k_attn_fwd<0, true, 0><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+    const char* mo = getenv("G3C_ATTN_TRACE_MMA_ONLY");  // stamps of the MMA warp only: no perturbation of the softmax warps
+    if (mode && mo && atoi(mo)) k_attn_fwd<0, 2, 2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+    else if (mode) k_attn_fwd<0, 1, 2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+    else k_attn_fwd<0, 1, 0, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
   } else if (mode == 0) {
-    k_attn_fwd<0, false, 0><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+    k_attn_fwd<0, 0, 0, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
   } else if (poly) {
-    k_attn_fwd<4, false, 2><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+    k_attn_fwd<4, 0, 2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+  } else if (cluster) {
+    // CTA pairs along the query dimension (grid.x padded to even: a padding CTA works on zero-filled Q rows and
+    // stores nothing) sharing every K / V tile through TMA multicast
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((grid.x + 1) & ~1u, grid.y);
+    cfg.blockDim = dim3(ATT_THREADS);
+    cfg.dynamicSmemBytes = ATT_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 0, 2, true>, tmQ, tmK, tmV, p));
   } else {
-    k_attn_fwd<0, false, 2><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+    k_attn_fwd<0, 0, 2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
   }
   G3C_CUDA(cudaGetLastError());
   return G3C_OK;

@@ -272,10 +272,10 @@ __global__ void __launch_bounds__(128)
   cs[(size_t)tok * 128 + 64 + j] = s;
 }
 
-__global__ void k_bf16_to_f32(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
+__global__ void k_bf16_to_f32(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n, float scale) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x)
-    out[i] = __bfloat162float(in[i]);
+    out[i] = __bfloat162float(in[i]) * scale;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -402,8 +402,8 @@ int rope_table(const float* freqs, int nt, int nh, int nw, int t0, float t_scale
   return G3C_OK;
 }
 
-int bf16_to_f32(const __nv_bfloat16* in, float* out, size_t n, cudaStream_t st) {
-  k_bf16_to_f32<<<(int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024), 256, 0, st>>>(in, out, n);
+int bf16_to_f32(const __nv_bfloat16* in, float* out, size_t n, cudaStream_t st, float scale) {
+  k_bf16_to_f32<<<(int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024), 256, 0, st>>>(in, out, n, scale);
   G3C_CUDA(cudaGetLastError());
   return G3C_OK;
 }

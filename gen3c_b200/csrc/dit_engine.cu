@@ -145,6 +145,9 @@ struct g3c_dit {
 
 namespace g3c {
 
+// softmax scale 1/sqrt(head_dim) times log2(e), folded into the query RMSNorm gain (see resolve())
+constexpr float kQScale = 0.08838834764831845f * 1.4426950408889634f;
+
 static const WTensor* find(const g3c_dit* h, const std::string& name) {
   auto it = h->w.find(name);
   return it == h->w.end() ? nullptr : &it->second;
@@ -240,7 +243,10 @@ static int resolve(g3c_dit* h, cudaStream_t st) {
         TRY(need_bf16(h, p + "block.attn.to_q.1.weight", {128}, &gq));
         TRY(need_bf16(h, p + "block.attn.to_k.1.weight", {128}, &gk));
         float* dst = h->gammas + (size_t)(i * 4 + j * 2) * 128;
-        TRY(bf16_to_f32(gq, dst, 128, st));
+        // the query gain also carries the softmax scale and log2(e): the attention kernel then receives its scores
+        // in log2 units (scale = ln 2 below) and its fast tiles need no multiply-subtract per score.  RoPE is a
+        // rotation, so the factor commutes with it.
+        TRY(bf16_to_f32(gq, dst, 128, st, kQScale));
         TRY(bf16_to_f32(gk, dst + 128, 128, st));
         s.gq = dst;
         s.gk = dst + 128;
@@ -300,7 +306,7 @@ static int forward(g3c_dit* h, const void* x_in, const void* cond_mask, const vo
   const g3c_dit_config& c = h->cfg;
   const int D = c.model_channels, R = c.adaln_lora_dim, F = c.ffn_dim, L = h->L, heads = c.num_heads;
   const int Lk_all = L * h->cp_size;
-  const float attn_scale = 1.0f / sqrtf(128.0f);
+  const float attn_scale = 0.6931471805599453f;  // ln 2: 1/sqrt(128) * log2(e) is folded into the query RMSNorm gain
   int n = 0;
 
   // ---- input assembly + patch embedding (general_dit_video_conditioned.py:112-118,

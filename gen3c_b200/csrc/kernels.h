@@ -45,7 +45,7 @@ int abs_pos(const __nv_bfloat16* pt, const __nv_bfloat16* ph, const __nv_bfloat1
             int Hp, int Wp, int D, __nv_bfloat16* out, cudaStream_t st);
 int rope_table(const float* freqs, int nt, int nh, int nw, int t0, float t_scale, int T, int Hp, int Wp,
                float* cs, cudaStream_t st);
-int bf16_to_f32(const __nv_bfloat16* in, float* out, size_t n, cudaStream_t st);
+int bf16_to_f32(const __nv_bfloat16* in, float* out, size_t n, cudaStream_t st, float scale = 1.0f);
 int sampler_pre(const __nv_bfloat16* xt, const __nv_bfloat16* gt, const float* noise, const float* ind_t,
                 int C, int T, size_t plane, float sigma, float sigma_aug, float sd,
                 __nv_bfloat16* xtilde, __nv_bfloat16* xin, cudaStream_t st);

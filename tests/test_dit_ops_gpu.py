@@ -128,6 +128,21 @@ def test_attention_score_jump(jump):
     assert rel(o, ref) < 5e-3, rel(o, ref)
 
 
+@pytest.mark.parametrize("gain", [1.0, 6.0])
+def test_attention_log2_units(gain):
+    """scale = ln 2: the caller folded softmax_scale * log2(e) into Q (what the DiT engine does through the query
+    RMSNorm gain), so S arrives in log2 units.  gain=1: first-tile row maxima within 2^+-40 -> the fast tiles use
+    p = 2^s with no reference subtraction; gain=6: maxima beyond 2^40 -> the kernel keeps a reference exponent."""
+    from gen3c_b200 import ops
+
+    heads, Lq, Lk = 2, 512, 2048
+    q, k, v = bf(Lq, heads * 128, seed=30, s=gain), bf(Lk, heads * 128, seed=31, s=gain), bf(Lk, heads * 128, seed=32)
+    qs = (q.float() * (128 ** -0.5 * math.log2(math.e))).to(torch.bfloat16)
+    ref = sdpa_ref(qs.float() * math.log(2.0) * 128 ** 0.5, k, v, heads)  # softmax(qs k^T ln2) == softmax(q k^T / sqrt(d))
+    o = ops.attention(qs, k, v.T.contiguous(), heads, scale=math.log(2.0))
+    assert rel(o, ref) < 5e-3, rel(o, ref)
+
+
 def test_ln_modulate():
     from gen3c_b200 import ops
 

@@ -1,6 +1,7 @@
 """Kernel-level timings at BASELINE sizes (CUDA events, warm-up, L2 flushed between iterations).
 Usage: python tools/gpu_perf.py [gemm] [attn] [warp] [eltwise]  -> JSON lines on stdout."""
 import json
+import os
 import sys
 import time
 
@@ -64,10 +65,17 @@ def attn_cases():
                                 ("cross 56320 x 512", 56320, 512, 32)]:
         D = heads * 128
         q, k, vt = bf(Lq, D), bf(Lk, D), bf(D, Lk)
-        med, best = timeit(lambda: ops.attention(q, k, vt, heads), iters=3, warm=1)
+        # G3C_PERF_LOG2=1: the engine's calling convention (softmax scale * log2 e folded into Q, scale = ln 2)
+        log2u = os.environ.get("G3C_PERF_LOG2", "0") == "1"
+        if log2u:
+            q = (q.float() * (128 ** -0.5 * 1.4426950408889634)).to(torch.bfloat16)
+        sc = 0.6931471805599453 if log2u else None
+        med, best = timeit(lambda: ops.attention(q, k, vt, heads, scale=sc), iters=3, warm=1)
         fl = 4.0 * Lq * Lk * D
         rec = {"kernel": "attn", "case": name, "ms": med, "ms_best": best, "tflops": fl / med / 1e9}
         try:
+            if os.environ.get("G3C_PERF_FAST", "0") == "1":
+                raise RuntimeError("skipped")
             qh = q.reshape(Lq, heads, 128).permute(1, 0, 2)[None]
             kh = k.reshape(Lk, heads, 128).permute(1, 0, 2)[None]
             vh = vt.T.reshape(Lk, heads, 128).permute(1, 0, 2)[None].contiguous()
