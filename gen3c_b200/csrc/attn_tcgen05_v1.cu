@@ -577,7 +577,7 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
   }
   // G3C_ATTN_MODE: softmax variant (see k_attn_fwd), 2 = sum-guarded reference (default), 0 = exact max per tile;
   // G3C_ATTN_POLY=4: every 4th exponential on the FMA pipe (measured slower, kept for A/B runs)
-  static int poly = -1, mode = 2, cluster = 0;
+  static int poly = -1, mode = 2, cluster = 1;
   if (poly < 0) {
     const char* e = getenv("G3C_ATTN_POLY");
     poly = (e && atoi(e) != 0) ? 4 : 0;
@@ -591,7 +591,7 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     e = getenv("G3C_ATTN_CLUSTER");
-    cluster = e ? atoi(e) != 0 : 0;
+    cluster = e ? atoi(e) != 0 : 1;
   }
   AttnParams p;
   p.Lq = Lq;

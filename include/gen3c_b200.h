@@ -101,7 +101,10 @@ int g3c_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, in
  * also usable as an `attn_op`, :136-139).
  *   q [Lq, heads*128] (ld ldq), k [Lk, heads*128] (ld ldk), vt [Lk/vt_chunk_len][heads*128]
  *   [vt_chunk_len] (V transposed, keys contiguous; vt_chunk_len <= 0 means Lk), o [Lq, heads*128].
- *   Lk must be a multiple of 128. */
+ *   Lk must be a multiple of 128.
+ *   scale = ln 2 (0.6931472) declares that Q already carries softmax_scale * log2(e) (the DiT engine folds it into
+ *   the query RMSNorm gain): the scores are then exponentiated as 2^s without a multiply per score.
+ *   block_n of g3c_gemm_bf16: 512 selects the CTA-pair kernel (256 x 256 tile), 0 chooses by wave count. */
 int g3c_attn_fwd(const void* q, const void* k, const void* vt, void* o, int Lq, int Lk, int heads,
                  int ldq, int ldk, int ldo, int vt_chunk_len, float scale, void* stream);
 

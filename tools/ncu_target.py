@@ -16,9 +16,10 @@ def bf(*s, sc=1.0):
 
 if which == "attn":
     L, H = 56320, 32
-    q, k, vt = bf(L, H * 128), bf(L, H * 128), bf(H * 128, L)
+    # the engine's calling convention: softmax scale * log2(e) folded into Q, scale = ln 2
+    q, k, vt = bf(L, H * 128, sc=128 ** -0.5 * 1.4426950408889634), bf(L, H * 128), bf(H * 128, L)
     for _ in range(2):
-        o = ops.attention(q, k, vt, H)
+        o = ops.attention(q, k, vt, H, scale=0.6931471805599453)
 elif which == "gemm":
     L = 56320
     a, w = bf(L, 4096), bf(4096, 4096, sc=0.02)
