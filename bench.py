@@ -278,7 +278,7 @@ def run_ours(args):
         "e2e": {"value": 1e3 / ms_e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "tensor", "kernel": "k_attn_fwd (self-attention)", "achieved": achieved, "peak": peak,
-                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + " (sustained)",
+                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(), "peak_source": peaks["source"] + " (sustained)",
                      "step_tflops": FLOP_PER_STEP * sps / 1e12 / world, "step_frac": FLOP_PER_STEP * sps / 1e12 / world / peak},
         "kernel_breakdown": breakdown,
         "clocks": clk,
@@ -295,6 +295,26 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic_bytes():
+    """DRAM bytes (read + write) of one full-size self-attention launch, from the committed `ncu --set full` summary
+    (profiles/r01_attn_ncu_summary.txt); None when the summary is absent.  Static evidence, not measured by this run."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_attn_ncu_summary.txt")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    tot, seen = 0.0, 0
+    try:
+        for ln in open(path):
+            if ln.startswith("--") and seen >= 2:
+                break
+            for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                if ln.startswith(key):
+                    unit = ln[ln.index("[") + 1:ln.index("]")]
+                    tot += float(ln.split("=")[1]) * scale[unit]
+                    seen += 1
+    except (OSError, ValueError, KeyError):
+        return None
+    return tot if seen >= 2 else None
 
 
 def main():

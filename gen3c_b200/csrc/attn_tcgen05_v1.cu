@@ -624,9 +624,10 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     k_attn_fwd<0, 0, 0, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
   } else if (poly) {
     k_attn_fwd<4, 0, 2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
-  } else if (cluster) {
-    // CTA pairs along the query dimension (grid.x padded to even: a padding CTA works on zero-filled Q rows and
-    // stores nothing) sharing every K / V tile through TMA multicast
+  } else if (cluster && (grid.x % 2 == 0 || grid.x < 16)) {
+    // CTA pairs along the query dimension sharing every K / V tile through TMA multicast.  An odd number of query
+    // blocks would need a padding CTA (zero-filled Q rows, stores nothing): worth it only for small grids, where it
+    // keeps this path covered by the unit tests; e.g. 55 blocks at cp = 4 run unpaired instead.
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((grid.x + 1) & ~1u, grid.y);
     cfg.blockDim = dim3(ATT_THREADS);

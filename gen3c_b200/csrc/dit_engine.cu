@@ -373,21 +373,27 @@ static int forward(g3c_dit* h, const void* x_in, const void* cond_mask, const vo
           ++n;
         } else {
           // default: produce locally, then the copy engines push the two slices to every peer on a side stream while
-          // this stream already runs the Q projection and attention over the local chunk; the flag that opens a
-          // remote chunk on a peer is raised (system scope) after all of this rank's copies have completed.
+          // this stream already runs the Q projection and attention over the local chunk.  Peer (me-1) is served
+          // first, then (me-2), ...: rank c consumes chunk c+1 first, so its k-th remote chunk is the k-th push of
+          // its producer.  The flag that opens the chunk on a peer follows that peer's two copies on the same stream
+          // (a 4-byte copy from a pinned ring: no kernel, see seq_ring).
           K(CAT_GEMM, gemm_bf16(h->xn, s.wk, kl, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
           K(CAT_ELTWISE, rmsnorm_rope(kl, D, L, heads, s.gk, h->rope, 1e-6f, st));
           K(CAT_GEMM, gemm_bf16(s.wv, h->xn, vl, D, L, D, D, D, L, G3C_EPI_BF16, nullptr, 0, st));  // V^T
           G3C_CUDA(cudaEventRecord(h->ev_kv, st));
           G3C_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_kv, 0));
-          for (int i2 = 0; i2 < pk.n; ++i2) {
-            G3C_CUDA(cudaMemcpyAsync(pk.ptr[i2], kl, slice, cudaMemcpyDeviceToDevice, h->comm_stream));
-            G3C_CUDA(cudaMemcpyAsync(pv.ptr[i2], vl, slice, cudaMemcpyDeviceToDevice, h->comm_stream));
-          }
           uint32_t* slot = h->seq_ring + (seq % g3c_dit::kSeqRing);
-          *slot = seq;  // read by the copy engine when the copies above have completed
-          for (int i2 = 0; i2 < pf.n; ++i2)
-            G3C_CUDA(cudaMemcpyAsync(pf.ptr[i2], slot, 4, cudaMemcpyHostToDevice, h->comm_stream));
+          *slot = seq;  // read by the copy engine when the copies queued before it have completed
+          for (int i2 = 1; i2 < h->cp_size; ++i2) {
+            const int r = (me - i2 + h->cp_size) % h->cp_size;
+            char* pb = (char*)h->peer_base[r];
+            G3C_CUDA(cudaMemcpyAsync(pb + h->off_k[set] + (size_t)me * slice, kl, slice, cudaMemcpyDeviceToDevice,
+                                     h->comm_stream));
+            G3C_CUDA(cudaMemcpyAsync(pb + h->off_vt[set] + (size_t)me * slice, vl, slice, cudaMemcpyDeviceToDevice,
+                                     h->comm_stream));
+            G3C_CUDA(cudaMemcpyAsync(pb + h->off_flags + (size_t)(set * 8 + me) * 4, slot, 4, cudaMemcpyHostToDevice,
+                                     h->comm_stream));
+          }
         }
         K(CAT_GEMM, gemm_bf16(h->xn, s.wq, h->q, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
         K(CAT_ELTWISE, rmsnorm_rope(h->q, D, L, heads, s.gq, h->rope, 1e-6f, st));
