@@ -80,8 +80,23 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
+// G3C_MBAR_SUSPEND_NS: suspend-time hint of mbarrier.try_wait — the thread may sleep that long before the instruction
+// returns false (it still wakes as soon as the phase completes), so a waiting warp re-issues the poll loop less often.
+// Measured with 20 us on the attention kernel: 1 219 / 1 241 against 1 240 / 1 255 TFLOP/s without — off by default.
+#ifndef G3C_MBAR_SUSPEND_NS
+#define G3C_MBAR_SUSPEND_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#if G3C_MBAR_SUSPEND_NS > 0
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)G3C_MBAR_SUSPEND_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
@@ -89,6 +104,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 // Spin with a generous bound so that a protocol bug traps instead of hanging the GPU box.
