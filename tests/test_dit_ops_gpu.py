@@ -96,11 +96,13 @@ def test_attention(Lq, Lk, heads, chunks):
     assert rel(o, ref) < 5e-3, rel(o, ref)
 
 
-def test_attention_peaked_softmax():
-    """Large logits: exercises the running-max rescale of O (scores spread over ~+-40)."""
+@pytest.mark.parametrize("Lk", [1024, 2048])
+def test_attention_peaked_softmax(Lk):
+    """Large logits: exercises the rescale of O (scores spread over ~+-40).  Lk <= 1024 runs the exact kernel (row max
+    per tile), longer key ranges the default one (reference shifted by the row sums)."""
     from gen3c_b200 import ops
 
-    heads, Lq, Lk = 1, 256, 1024
+    heads, Lq = 1, 256
     q, k, v = bf(Lq, 128, seed=10, s=3.0), bf(Lk, 128, seed=11, s=3.0), bf(Lk, 128, seed=12)
     # make later keys systematically larger so the max keeps growing across KV tiles
     k = (k.float() * torch.linspace(0.2, 2.0, Lk, device="cuda")[:, None]).to(torch.bfloat16)
@@ -118,7 +120,7 @@ def test_attention_score_jump(jump):
     G3C_ATTN_MODE=0."""
     from gen3c_b200 import ops
 
-    heads, Lq, Lk = 2, 384, 1024
+    heads, Lq, Lk = 2, 384, 2048  # > 1024 keys: the default (sum-guarded) kernel, not the short-range exact one
     q, k, v = bf(Lq, heads * 128, seed=20, s=0.5), bf(Lk, heads * 128, seed=21, s=0.5), bf(Lk, heads * 128, seed=22)
     q[:, :128] = 1.0  # head 0: constant queries; head 1 stays random
     k[300:340, :128] = jump  # scores 128 * jump / sqrt(128) = 11.3 * jump nats above the rest, in KV tile 2
