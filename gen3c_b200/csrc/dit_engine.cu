@@ -307,6 +307,36 @@ static int forward(g3c_dit* h, const void* x_in, const void* cond_mask, const vo
   const int D = c.model_channels, R = c.adaln_lora_dim, F = c.ffn_dim, L = h->L, heads = c.num_heads;
   const int Lk_all = L * h->cp_size;
   const float attn_scale = 0.6931471805599453f;  // ln 2: 1/sqrt(128) * log2(e) is folded into the query RMSNorm gain
+  // to_q / to_k: Linear + per-head RMSNorm (+ RoPE).  Fused into the GEMM epilogue (G3C_FUSE_NORM_ROPE, default on):
+  // the norm and the rotation act on the fp32 accumulators in TMEM and the [tokens, D] bf16 round trip of a separate
+  // pass disappears.
+  static int fuse_nr = -1;
+  if (fuse_nr < 0) {
+    const char* e = getenv("G3C_FUSE_NORM_ROPE");
+    fuse_nr = e ? atoi(e) != 0 : 1;
+  }
+  auto proj_norm_rope = [&](const void* a, const void* w, __nv_bfloat16* out, int M, int Kin,
+                            const float* gamma, const float* cs, int& launches) -> int {
+    if (fuse_nr) {
+      NormRope nr;
+      nr.gamma = gamma;
+      nr.cs = cs;
+      nr.eps = 1e-6f;
+      TRY(prof_mark(h, CAT_GEMM, true, st));
+      TRY(gemm_bf16(a, w, out, M, D, Kin, Kin, Kin, D, G3C_EPI_BF16, nullptr, 0, st, nullptr, &nr));
+      TRY(prof_mark(h, CAT_GEMM, false, st));
+      launches += 1;
+    } else {
+      TRY(prof_mark(h, CAT_GEMM, true, st));
+      TRY(gemm_bf16(a, w, out, M, D, Kin, Kin, Kin, D, G3C_EPI_BF16, nullptr, 0, st));
+      TRY(prof_mark(h, CAT_GEMM, false, st));
+      TRY(prof_mark(h, CAT_ELTWISE, true, st));
+      TRY(rmsnorm_rope(out, D, M, heads, gamma, cs, 1e-6f, st));
+      TRY(prof_mark(h, CAT_ELTWISE, false, st));
+      launches += 2;
+    }
+    return G3C_OK;
+  };
   int n = 0;
 
   // ---- input assembly + patch embedding (general_dit_video_conditioned.py:112-118,
@@ -377,8 +407,7 @@ static int forward(g3c_dit* h, const void* x_in, const void* cond_mask, const vo
           // first, then (me-2), ...: rank c consumes chunk c+1 first, so its k-th remote chunk is the k-th push of
           // its producer.  The flag that opens the chunk on a peer follows that peer's two copies on the same stream
           // (a 4-byte copy from a pinned ring: no kernel, see seq_ring).
-          K(CAT_GEMM, gemm_bf16(h->xn, s.wk, kl, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
-          K(CAT_ELTWISE, rmsnorm_rope(kl, D, L, heads, s.gk, h->rope, 1e-6f, st));
+          TRY(proj_norm_rope(h->xn, s.wk, kl, L, D, s.gk, h->rope, n));
           K(CAT_GEMM, gemm_bf16(s.wv, h->xn, vl, D, L, D, D, D, L, G3C_EPI_BF16, nullptr, 0, st));  // V^T
           G3C_CUDA(cudaEventRecord(h->ev_kv, st));
           G3C_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_kv, 0));
@@ -395,16 +424,14 @@ static int forward(g3c_dit* h, const void* x_in, const void* cond_mask, const vo
                                      h->comm_stream));
           }
         }
-        K(CAT_GEMM, gemm_bf16(h->xn, s.wq, h->q, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
-        K(CAT_ELTWISE, rmsnorm_rope(h->q, D, L, heads, s.gq, h->rope, 1e-6f, st));
+        TRY(proj_norm_rope(h->xn, s.wq, h->q, L, D, s.gq, h->rope, n));
         ChunkGate gate;
         gate.flags = (const uint32_t*)(reg + h->off_flags) + set * 8;
         gate.seq = seq;
         gate.first = me;
         K(CAT_ATTN_SELF, attn_fwd(h->q, kb, vb, h->att, L, Lk_all, heads, D, D, D, L, attn_scale, st, &gate));
       } else {
-        K(CAT_GEMM, gemm_bf16(h->xn, s.wk, k_loc, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
-        K(CAT_ELTWISE, rmsnorm_rope(k_loc, D, L, heads, s.gk, h->rope, 1e-6f, st));
+        TRY(proj_norm_rope(h->xn, s.wk, k_loc, L, D, s.gk, h->rope, n));
         K(CAT_GEMM, gemm_bf16(s.wv, h->xn, vt_loc, D, L, D, D, D, L, G3C_EPI_BF16, nullptr, 0, st));  // V^T
         if (h->cp_size > 1) {
           // baseline mode (G3C_CP_MODE=nccl): one in-place all-gather of K and of V^T per layer on a side stream
@@ -417,8 +444,7 @@ static int forward(g3c_dit* h, const void* x_in, const void* cond_mask, const vo
           G3C_CUDA(cudaEventRecord(h->ev_gathered, h->comm_stream));
           n += 2;
         }
-        K(CAT_GEMM, gemm_bf16(h->xn, s.wq, h->q, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
-        K(CAT_ELTWISE, rmsnorm_rope(h->q, D, L, heads, s.gq, h->rope, 1e-6f, st));
+        TRY(proj_norm_rope(h->xn, s.wq, h->q, L, D, s.gq, h->rope, n));
         if (h->cp_size > 1) G3C_CUDA(cudaStreamWaitEvent(st, h->ev_gathered, 0));
         K(CAT_ATTN_SELF, attn_fwd(h->q, h->k_all, h->vt_all, h->att, L, Lk_all, heads, D, D, D, L, attn_scale, st));
       }
@@ -430,11 +456,9 @@ static int forward(g3c_dit* h, const void* x_in, const void* cond_mask, const vo
       const float* m = h->mods + (size_t)(i * 3 + 1) * 3 * D;
       const int C = c.context_dim, M = h->ctx_len;
       K(CAT_ELTWISE, ln_modulate(h->x, nullptr, m, m + D, h->xn, L, D, 1e-6f, st));
-      K(CAT_GEMM, gemm_bf16(ctx, s.wk, h->kc, M, D, C, C, C, D, G3C_EPI_BF16, nullptr, 0, st));
-      K(CAT_ELTWISE, rmsnorm_rope(h->kc, D, M, heads, s.gk, nullptr, 1e-6f, st));
+      TRY(proj_norm_rope(ctx, s.wk, h->kc, M, C, s.gk, nullptr, n));
       K(CAT_GEMM, gemm_bf16(s.wv, ctx, h->vtc, D, M, C, C, C, M, G3C_EPI_BF16, nullptr, 0, st));
-      K(CAT_GEMM, gemm_bf16(h->xn, s.wq, h->q, L, D, D, D, D, D, G3C_EPI_BF16, nullptr, 0, st));
-      K(CAT_ELTWISE, rmsnorm_rope(h->q, D, L, heads, s.gq, nullptr, 1e-6f, st));
+      TRY(proj_norm_rope(h->xn, s.wq, h->q, L, D, s.gq, nullptr, n));
       K(CAT_ATTN_CROSS, attn_fwd(h->q, h->kc, h->vtc, h->att, L, M, heads, D, D, D, M, attn_scale, st));
       K(CAT_GEMM, gemm_bf16(h->att, s.wo, h->x, L, D, D, D, D, D, G3C_EPI_GATED_RESIDUAL_F32, m + 2 * D, 0, st));
     }

@@ -34,7 +34,16 @@ struct GemmParams {
   int super_n;         // n-blocks per super-column (L2 reuse of the B operand)
   int n_peer;          // bf16 epilogues: additional destinations (peer GPUs), same offsets as D
   void* peer[7];
+  // EPI_NORM_ROPE_BF16: per-head (128 columns) RMSNorm gain [128], cos|sin table [M][128] (or NULL: no rotation), eps
+  const float* nr_gamma;
+  const float* nr_cs;
+  float nr_eps;
 };
+
+// internal epilogue (not part of the C ABI enum; reached through gemm_bf16(..., norm_rope)):
+// D (bf16) = RoPE(RMSNorm_head(acc) * gamma) — the to_q / to_k Sequential(Linear, RMSNorm) of the reference followed by
+// the rotate-half RoPE, applied to the fp32 accumulators of one head while they are still in TMEM.
+constexpr int EPI_NORM_ROPE_BF16 = 4;
 
 template <int BN>
 struct GemmSmem {
@@ -66,6 +75,70 @@ __device__ __forceinline__ void tile_coords(const GemmParams& p, int tile, int& 
   } else {
     m_blk = rem / p.super_n;
     n_blk = n0 + rem - m_blk * p.super_n;
+  }
+}
+
+// Fused Linear -> per-head RMSNorm -> rotate-half RoPE for one head (128 accumulator columns at TMEM address `taddr`,
+// lane = row).  Pass 1 reduces the sum of squares, pass 2 re-reads the columns in (c, c + 64) pairs — the rotate-half
+// partners — scales, rotates and stores two 64-byte row segments.  reference: module/attention.py:263-266 (to_q/to_k
+// = Linear + RMSNorm) and :268-283 (apply_rotary_pos_emb); same arithmetic as k_rmsnorm_rope (dit_elementwise.cu).
+__device__ __forceinline__ void epilogue_norm_rope_head(uint32_t taddr, const GemmParams& p, int row, int col0) {
+  float ss = 0.0f;
+#pragma unroll 1
+  for (int cc = 0; cc < 4; ++cc) {
+    uint32_t r[32];
+    tmem_ld32(taddr + cc * 32, r);
+    tc_wait_ld();
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s4[i & 3] = fmaf(__uint_as_float(r[i]), __uint_as_float(r[i]), s4[i & 3]);
+    ss += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  }
+  const float rstd = rsqrtf(ss * (1.0f / 128.0f) + p.nr_eps);
+  const bool row_ok = row < p.M;
+  const float* cs = p.nr_cs ? p.nr_cs + (size_t)(row_ok ? row : 0) * 128 : nullptr;
+  __nv_bfloat16* dptr = reinterpret_cast<__nv_bfloat16*>(p.D) + (size_t)row * p.ldd + col0;
+#pragma unroll 1
+  for (int cc = 0; cc < 2; ++cc) {
+    uint32_t ra[32], rb[32];
+    tmem_ld32(taddr + cc * 32, ra);
+    tmem_ld32(taddr + 64 + cc * 32, rb);
+    tc_wait_ld();
+    uint4 qa[4], qb[4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // 4 columns per step
+      const int c = cc * 32 + 4 * j;
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(p.nr_gamma + c));
+      const float4 gb = __ldg(reinterpret_cast<const float4*>(p.nr_gamma + 64 + c));
+      float a[4] = {__uint_as_float(ra[4 * j]) * (rstd * ga.x), __uint_as_float(ra[4 * j + 1]) * (rstd * ga.y),
+                    __uint_as_float(ra[4 * j + 2]) * (rstd * ga.z), __uint_as_float(ra[4 * j + 3]) * (rstd * ga.w)};
+      float b[4] = {__uint_as_float(rb[4 * j]) * (rstd * gb.x), __uint_as_float(rb[4 * j + 1]) * (rstd * gb.y),
+                    __uint_as_float(rb[4 * j + 2]) * (rstd * gb.z), __uint_as_float(rb[4 * j + 3]) * (rstd * gb.w)};
+      if (cs) {
+        const float4 co = *reinterpret_cast<const float4*>(cs + c);
+        const float4 si = *reinterpret_cast<const float4*>(cs + 64 + c);
+        const float cv[4] = {co.x, co.y, co.z, co.w}, sv[4] = {si.x, si.y, si.z, si.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float n = a[e] * cv[e] - b[e] * sv[e], m = b[e] * cv[e] + a[e] * sv[e];
+          a[e] = n;
+          b[e] = m;
+        }
+      }
+      uint32_t* pa = reinterpret_cast<uint32_t*>(&qa[j >> 1]) + (j & 1) * 2;
+      uint32_t* pb = reinterpret_cast<uint32_t*>(&qb[j >> 1]) + (j & 1) * 2;
+      pa[0] = pack_bf16x2(a[0], a[1]);
+      pa[1] = pack_bf16x2(a[2], a[3]);
+      pb[0] = pack_bf16x2(b[0], b[1]);
+      pb[1] = pack_bf16x2(b[2], b[3]);
+    }
+    if (row_ok) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        reinterpret_cast<uint4*>(dptr + cc * 32)[i] = qa[i];
+        reinterpret_cast<uint4*>(dptr + 64 + cc * 32)[i] = qb[i];
+      }
+    }
   }
 }
 
@@ -261,13 +334,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       tile_coords(p, tile, m_blk, n_blk);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
+      if constexpr (EPI == EPI_NORM_ROPE_BF16) {
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((ew * 32u) << 16) + as * BN + c * 32, r);
-        tc_wait_ld();
-        epilogue_chunk<EPI>(r, p, &tmD, m_blk * BM + (int)ew * 32, n_blk * BN + c * 32, lane,
-                            stage_f32 + ew * 2 * 4096, ebuf);
+        for (int hd = 0; hd < BN / 128; ++hd)
+          if (n_blk * BN + hd * 128 < p.N)
+            epilogue_norm_rope_head(tmem_base + ((ew * 32u) << 16) + as * BN + hd * 128, p,
+                                    m_blk * BM + (int)ew * 32 + (int)lane, n_blk * BN + hd * 128);
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((ew * 32u) << 16) + as * BN + c * 32, r);
+          tc_wait_ld();
+          epilogue_chunk<EPI>(r, p, &tmD, m_blk * BM + (int)ew * 32, n_blk * BN + c * 32, lane,
+                              stage_f32 + ew * 2 * 4096, ebuf);
+        }
       }
       tc_fence_before();
       mbar_arrive(&tempty[as]);
@@ -415,13 +496,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
       tile_coords(p, tile, m_blk, n_blk);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
+      if constexpr (EPI == EPI_NORM_ROPE_BF16) {
 #pragma unroll 1
-      for (int c = 0; c < BN2 / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((ew * 32u) << 16) + as * BN2 + c * 32, r);
-        tc_wait_ld();
-        epilogue_chunk<EPI>(r, p, &tmD, m_blk * 256 + (int)cta * 128 + (int)ew * 32, n_blk * BN2 + c * 32, lane,
-                            stage_f32 + ew * 2 * 4096, ebuf);
+        for (int hd = 0; hd < BN2 / 128; ++hd)
+          epilogue_norm_rope_head(tmem_base + ((ew * 32u) << 16) + as * BN2 + hd * 128, p,
+                                  m_blk * 256 + (int)cta * 128 + (int)ew * 32 + (int)lane, n_blk * BN2 + hd * 128);
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN2 / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((ew * 32u) << 16) + as * BN2 + c * 32, r);
+          tc_wait_ld();
+          epilogue_chunk<EPI>(r, p, &tmD, m_blk * 256 + (int)cta * 128 + (int)ew * 32, n_blk * BN2 + c * 32, lane,
+                              stage_f32 + ew * 2 * 4096, ebuf);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -465,6 +553,7 @@ static int dispatch_epi2(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB
     case G3C_EPI_GELU_BF16: return launch_gemm2<G3C_EPI_GELU_BF16>(tmA, tmB, tmD, p, st);
     case G3C_EPI_GATED_RESIDUAL_F32: return launch_gemm2<G3C_EPI_GATED_RESIDUAL_F32>(tmA, tmB, tmD, p, st);
     case G3C_EPI_F32: return launch_gemm2<G3C_EPI_F32>(tmA, tmB, tmD, p, st);
+    case EPI_NORM_ROPE_BF16: return launch_gemm2<EPI_NORM_ROPE_BF16>(tmA, tmB, tmD, p, st);
   }
   set_error("gemm: unknown epilogue %d", epi);
   return G3C_EINVAL;
@@ -495,6 +584,9 @@ static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
     case G3C_EPI_GELU_BF16: return launch_gemm<BN, G3C_EPI_GELU_BF16>(tmA, tmB, tmD, p, st);
     case G3C_EPI_GATED_RESIDUAL_F32: return launch_gemm<BN, G3C_EPI_GATED_RESIDUAL_F32>(tmA, tmB, tmD, p, st);
     case G3C_EPI_F32: return launch_gemm<BN, G3C_EPI_F32>(tmA, tmB, tmD, p, st);
+    case EPI_NORM_ROPE_BF16:
+      if constexpr (BN >= 128) return launch_gemm<BN, EPI_NORM_ROPE_BF16>(tmA, tmB, tmD, p, st);
+      break;
   }
   set_error("gemm: unknown epilogue %d", epi);
   return G3C_EINVAL;
@@ -502,14 +594,23 @@ static int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB,
 
 // Host entry used by the engine and by the C ABI.
 int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
-              int epilogue, const float* gate, int block_n, cudaStream_t st, const PeerDst* peers) {
+              int epilogue, const float* gate, int block_n, cudaStream_t st, const PeerDst* peers,
+              const NormRope* norm_rope) {
   G3C_REQUIRE(A && B && D, "gemm: null operand");
+  if (norm_rope) {
+    G3C_REQUIRE(epilogue == G3C_EPI_BF16 && N % 128 == 0 && norm_rope->gamma && (!peers || peers->n == 0),
+                "gemm: the RMSNorm/RoPE epilogue needs the bf16 epilogue, N %% 128 == 0, a gain vector and no peers");
+    G3C_REQUIRE((reinterpret_cast<uintptr_t>(norm_rope->gamma) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(norm_rope->cs) & 15) == 0,
+                "gemm: RMSNorm gain / RoPE table must be 16-byte aligned");
+    epilogue = EPI_NORM_ROPE_BF16;
+  }
   G3C_REQUIRE(!peers || peers->n == 0 || (epilogue == G3C_EPI_BF16 && N % 32 == 0 && peers->n <= 7),
               "gemm: peer destinations need the bf16 epilogue, N %% 32 == 0 and at most 7 peers");
   G3C_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape %dx%dx%d", M, N, K);
   G3C_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, "gemm: K/lda/ldb must be multiples of 8");
   G3C_REQUIRE(lda >= K && ldb >= K && ldd >= N, "gemm: leading dimension smaller than extent");
-  if (epilogue == G3C_EPI_BF16 || epilogue == G3C_EPI_GELU_BF16)
+  if (epilogue == G3C_EPI_BF16 || epilogue == G3C_EPI_GELU_BF16 || epilogue == EPI_NORM_ROPE_BF16)
     G3C_REQUIRE(ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0,
                 "gemm: bf16 output needs ldd %% 8 == 0 and 16-byte aligned base");
   else
@@ -536,6 +637,7 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int ld
     bn = (100 * waves_p <= 106 * waves_s) ? 512 : 256;
   }
   if (bn == 0) bn = (N >= 256 && N % 256 == 0) ? 256 : (N > 64 ? 128 : 64);
+  G3C_REQUIRE(epilogue != EPI_NORM_ROPE_BF16 || bn >= 128, "gemm: the RMSNorm/RoPE epilogue needs tiles of whole heads");
   G3C_REQUIRE(bn == 64 || bn == 128 || bn == 256 || bn == 512, "gemm: block_n %d unsupported", bn);
   const bool pair = bn == 512;
   if (pair) {
@@ -571,6 +673,9 @@ int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int ld
   p.gate = gate;
   p.n_peer = peers ? peers->n : 0;
   for (int i = 0; i < 7; ++i) p.peer[i] = (peers && i < peers->n) ? peers->ptr[i] : nullptr;
+  p.nr_gamma = norm_rope ? norm_rope->gamma : nullptr;
+  p.nr_cs = norm_rope ? norm_rope->cs : nullptr;
+  p.nr_eps = norm_rope ? norm_rope->eps : 0.0f;
   p.num_m_blk = pair ? (M + 255) / 256 : (M + BM - 1) / BM;
   p.num_n_blk = (N + bn - 1) / bn;
   p.num_k_blk = (K + BK - 1) / BK;
@@ -595,4 +700,13 @@ extern "C" int g3c_gemm_bf16(const void* A, const void* B, void* D, int M, int N
                              void* stream) {
   return g3c::gemm_bf16(A, B, D, M, N, K, lda, ldb, ldd, epilogue, gate, block_n,
                         (cudaStream_t)stream, nullptr);
+}
+
+extern "C" int g3c_gemm_norm_rope_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb,
+                                       int ldd, const float* gamma, const float* cos_sin, float eps, void* stream) {
+  g3c::NormRope nr;
+  nr.gamma = gamma;
+  nr.cs = cos_sin;
+  nr.eps = eps;
+  return g3c::gemm_bf16(A, B, D, M, N, K, lda, ldb, ldd, G3C_EPI_BF16, nullptr, 0, (cudaStream_t)stream, nullptr, &nr);
 }

@@ -11,8 +11,17 @@ struct PeerDst {
   void* ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
+// Optional fused tail of a projection: per-head (128 columns) RMSNorm with gain `gamma` [128] and, when `cs` is given,
+// rotate-half RoPE with the cos|sin table `cs` [M][128] — applied to the fp32 accumulators in the GEMM epilogue.
+struct NormRope {
+  const float* gamma = nullptr;
+  const float* cs = nullptr;
+  float eps = 1e-6f;
+};
+
 int gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
-              int epilogue, const float* gate, int block_n, cudaStream_t st, const PeerDst* peers = nullptr);
+              int epilogue, const float* gate, int block_n, cudaStream_t st, const PeerDst* peers = nullptr,
+              const NormRope* norm_rope = nullptr);
 // Chunk-ordered attention for context parallelism: KV chunk c (= source rank) may only be read once
 // flags[c] >= seq (written with system scope by rank c after its K / V^T slices have landed here); chunks are
 // visited starting at `first` so that the local chunk overlaps the arrival of the remote ones.

@@ -41,6 +41,28 @@ def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int = EPI_BF16, out: Option
     return out
 
 
+def gemm_norm_rope(a: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, cos_sin: Optional[torch.Tensor] = None,
+                   eps: float = 1e-6) -> torch.Tensor:
+    """out[M,N] (bf16) = RoPE(RMSNorm_head(a @ b^T) * gamma): projection + per-head (128) RMSNorm + rotate-half RoPE in
+    one kernel (reference: to_q / to_k = Sequential(Linear, RMSNorm) + apply_rotary_pos_emb, module/attention.py:263-283).
+    gamma f32 [128]; cos_sin f32 [M, 128] (cos | sin of the 64 angles) or None."""
+    _chk(a, torch.bfloat16, "a")
+    _chk(b, torch.bfloat16, "b")
+    _chk(gamma, torch.float32, "gamma")
+    M, K = a.shape
+    N = b.shape[0]
+    assert b.shape[1] == K and N % 128 == 0 and gamma.numel() == 128
+    if cos_sin is not None:
+        _chk(cos_sin, torch.float32, "cos_sin")
+        assert tuple(cos_sin.shape) == (M, 128)
+    out = torch.empty((M, N), device=a.device, dtype=torch.bfloat16)
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        _lib.check(lib.g3c_gemm_norm_rope_bf16(_lib.ptr(a), _lib.ptr(b), _lib.ptr(out), M, N, K, K, K, N, _lib.ptr(gamma),
+                                               _lib.ptr(cos_sin), eps, _lib.stream_ptr()), "g3c_gemm_norm_rope_bf16")
+    return out
+
+
 def attention(q: torch.Tensor, k: torch.Tensor, vt: torch.Tensor, heads: int, scale: Optional[float] = None,
               vt_chunk_len: int = 0) -> torch.Tensor:
     """q [Lq, heads*128], k [Lk, heads*128], vt [chunks, heads*128, chunk_len] or [heads*128, Lk] (V transposed).

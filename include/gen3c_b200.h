@@ -96,6 +96,13 @@ int g3c_reliable_depth_mask(const float* depth, int b, int H, int W, int window,
 int g3c_gemm_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb,
                   int ldd, int epilogue, const float* gate, int block_n, void* stream);
 
+/* D (bf16) [M,N] = RoPE(RMSNorm_head(A . B^T) * gamma): the to_q / to_k projection of the reference
+ * (`nn.Sequential(Linear, RMSNorm)`, module/attention.py:263-266) followed by the rotate-half RoPE (:268-283), with the
+ * norm and the rotation applied to the fp32 accumulators of each 128-wide head in the GEMM epilogue.  gamma [128] f32,
+ * cos_sin [M][128] f32 (cos of the 64 angles | sin) or NULL for no rotation; N must be a multiple of 128. */
+int g3c_gemm_norm_rope_bf16(const void* A, const void* B, void* D, int M, int N, int K, int lda, int ldb, int ldd,
+                            const float* gamma, const float* cos_sin, float eps, void* stream);
+
 /* O = softmax(Q K^T * scale) V, head_dim 128, no mask — the attention operator behind
  * Attention.cal_attn (reference: module/attention.py:282-297, TE DotProductAttention :228-238;
  * also usable as an `attn_op`, :136-139).

@@ -73,6 +73,27 @@ def test_gemm_transposed_output_by_operand_swap():
     assert rel(vt, (x.float() @ w.float().T).T) < 3e-3
 
 
+@pytest.mark.parametrize("M,N,K,rope", [(1000, 256, 512, True), (512, 4096, 1024, False), (4096, 4096, 512, True),
+                                          (300, 128, 256, True)])
+def test_gemm_norm_rope(M, N, K, rope):
+    """Projection + per-head RMSNorm + RoPE in the GEMM epilogue (1-CTA and CTA-pair kernels) against the composition
+    gemm (fp32 out) -> oracle RMSNorm / RoPE."""
+    from gen3c_b200 import ops
+    from oracle import dit_oracle
+
+    a, b = bf(M, K, seed=41), bf(N, K, seed=42, s=0.05)
+    gamma = (1 + 0.1 * torch.randn(128, device="cuda")).contiguous()
+    ang = torch.rand(M, 64, device="cuda") * 6.0
+    cs = torch.cat([torch.cos(ang), torch.sin(ang)], dim=1).contiguous()
+    heads = N // 128
+    acc = (a.float() @ b.float().T).cpu()
+    ref = dit_oracle.rms_norm(acc.reshape(M, heads, 128), gamma.cpu())
+    if rope:
+        ref = dit_oracle.apply_rope(ref, torch.cat([ang, ang], 1).cpu())
+    got = ops.gemm_norm_rope(a, b, gamma, cs if rope else None)
+    assert rel(got.cpu(), ref.reshape(M, N)) < 3e-3, rel(got.cpu(), ref.reshape(M, N))
+
+
 def sdpa_ref(q, k, v, heads):
     Lq, D = q.shape
     qh = q.float().reshape(Lq, heads, 128).permute(1, 0, 2)
