@@ -1,4 +1,6 @@
-// Path D — non-causal multi-head attention forward, head_dim 128, on tcgen05 / TMEM.
+// Path D — non-causal multi-head attention forward, head_dim 128, on tcgen05 / TMEM: per-tile S buffers with P
+// aliasing S, A/B tile alternation.  (Variants that were built and measured slower — 64-key tiles with double-buffered
+// S, one shared S buffer with separate P columns, 16 softmax warps — are described in profiles/r01_attention_variants.txt.)
 //   O = softmax(Q K^T * scale) V        (reference: cosmos_predict1/diffusion/module/attention.py
 //   :282-297 `cal_attn` -> transformer_engine DotProductAttention(sbhd, no_mask, dropout 0);
 //   self-attention Lq = Lk = 56 320, cross-attention Lk = 512)
@@ -15,25 +17,26 @@
 //   warps 4-7  softmax of tile B
 //   warp  8    TMA producer: Q once, then K_j / V_j through a 4-slot ring of 32 KB tiles
 //   warp  9    TMEM allocator + single-thread MMA issuer
-// TMEM (512 columns): S [0,128) — ONE score buffer shared by both tiles —, P_A [128,192), P_B [192,256)
-// (bf16 probabilities, the TMEM A operand of the P·V MMA), O_A [256,384), O_B [384,512).
-// The round-1 profile of the first version (P aliasing a per-tile S buffer, profiles/r01_attn_ncu_summary.txt)
-// showed a strict A/B alternation: QK_X(j+1) could not be issued before PV_X(j) had consumed P_X(j), so each
-// tile paid softmax + MMA + two barrier hops in series (tensor pipe 52-56 %, softmax warps idle ~45 %).
-// Here a softmax thread copies its S row into registers and immediately hands the S buffer back (`s_free`);
-// P lives in its own columns, so the MMA issue order becomes
-//     QK_A(j+1) ; PV_A(j) ; QK_B(j+1) ; PV_B(j)
-// and S_X(j+1) is already waiting in TMEM when softmax X finishes tile j: both softmax warpgroups run back to
-// back (2 warps per SM sub-partition interleave MUFU and FMA work) while the tensor pipe never waits for them.
-// Online softmax keeps a lazily updated reference max: O / row-sum are only rescaled when the row max grew
-// by more than 2^8 (after PV(j-1) has committed), so the TMEM read-modify-write of O is rare.
+// TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,384) O_B [384,512); P (bf16) overwrites
+// the first 64 columns of its S tile and feeds the P·V MMA straight from TMEM.
+// MMA order per KV step j:  PV_A(j) ; S_A(j+1) ; PV_B(j) ; S_B(j+1)  — the S MMA of one tile and
+// the whole PV/S pair of the other overlap with that tile's softmax.  P is released to the MMA warp
+// in two 64-key halves, so the first four P·V k-steps run under the second half of the exponentials.
+// Per tile the dependent chain is  S MMA -> softmax -> PV MMA -> (P columns free) -> next S MMA, so
+// the softmax LATENCY of one tile, not its throughput, sets the step period (clock64 timelines:
+// profiles/r01_attn_v1_timeline.txt).  Hence (kMode 1): the row max is reduced in the shadow of the
+// exponentials of the first half, which speculatively use the previous reference max; O / row sum are
+// only rescaled (and that half recomputed) when the max grew past the lazy threshold — rare after
+// the first KV tiles; fp32x2 packed FFMA/FADD and 3-input max halve the non-MUFU issue slots.
+#include <cmath>
 #include <cstdlib>
 
 #include "kernels.h"
 
 namespace g3c {
+namespace v1 {
 
-constexpr int ATT_THREADS = 384;  // 3 warpgroups: softmax A, softmax B, {TMA, MMA, 2 idle}
+constexpr int ATT_THREADS = 320;
 constexpr int ATT_TILE = 128;             // rows per Q tile, keys per KV tile, head dim
 constexpr int ATT_HALF_BYTES = 128 * 128; // one 64-column half of a 128x128 bf16 tile
 constexpr int ATT_TILE_BYTES = 2 * ATT_HALF_BYTES;
@@ -46,6 +49,11 @@ struct AttnParams {
   int vt_chunk_len;
   __nv_bfloat16* O;
   float scale_log2;  // softmax scale * log2(e)
+  const uint32_t* chunk_flags;  // context-parallel gate (or NULL): chunk c readable once chunk_flags[c] >= flag_seq
+  uint32_t flag_seq;
+  int first_chunk;
+  int unit_scale;             // 1: scale_log2 == 1 (the caller folded softmax scale * log2 e into Q): S is in log2 units
+  int p_halves;               // 1: P is released to the MMA warp per 64-key half, 0: per 128-key tile
   unsigned long long* trace;  // kTrace only: [3 roles][64 steps][8 slots] clock64 stamps of CTA (0,0)
 };
 
@@ -62,6 +70,20 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {  // FADD2: two fp32 adds in one instruction
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
 // 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, rel. err 7.5e-5, far below the bf16
 // rounding of P): the MUFU unit delivers only 16 ex2/clk/SM, which is exactly as slow as the two MMAs of a
 // KV step; computing every kPolyEvery-th exponential here takes the softmax off the critical path.
@@ -74,7 +96,17 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
 }
 
-template <int kPolyEvery, bool kTrace>
+// kMode 0: exact row max of every KV tile -> lazy rescale -> exponentials.
+// kMode 2: the row max is only reduced for the first KV tile.  Afterwards the exponentials simply keep using the
+//          current reference exponent: fp32 (and bf16 P) carry 8 exponent bits, so a stale reference costs no
+//          precision, only range.  Range is guarded by the row sums that are computed anyway: when a tile's sum
+//          exceeds 2^16 the reference is shifted by that sum's exponent before the next tile (O and the running sum
+//          are scaled by an exact power of two); if a row sum still ends up non-finite — a jump of > 2^100 inside one
+//          tile — the CTA repeats its work once in the exact mode (second pass of the role loops below).
+//          The ~300 clk max reduction leaves the per-tile dependent chain (see the timeline in profiles/).
+// kCluster: the CTAs of two neighbouring query blocks of one head form a cluster; each TMA-loads HALF of every K / V
+//           tile and multicasts it into both CTAs' rings, so every K / V byte leaves L2 once per 512 query rows.
+template <int kPolyEvery, int kTrace, int kMode, bool kCluster>  // kTrace 1: stamps in every role, 2: MMA warp only
 __global__ void __launch_bounds__(ATT_THREADS, 1)
     k_attn_fwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -87,11 +119,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
   uint64_t* q_full = bars;                        // [1]
   uint64_t* kv_full = bars + 1;                   // [slots]
   uint64_t* kv_empty = bars + 1 + ATT_SLOTS;      // [slots]
-  uint64_t* s_full = bars + 1 + 2 * ATT_SLOTS;    // [2]  QK_t done          (tcgen05.commit)
-  uint64_t* p_full = bars + 3 + 2 * ATT_SLOTS;    // [2]  P_t stored         (128 softmax threads)
-  uint64_t* pv_done = bars + 5 + 2 * ATT_SLOTS;   // [2]  PV_t done          (tcgen05.commit)
-  uint64_t* s_free = bars + 7 + 2 * ATT_SLOTS;    // [1]  S copied to registers (128 softmax threads)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8 + 2 * ATT_SLOTS);
+  uint64_t* s_full = bars + 1 + 2 * ATT_SLOTS;    // [2]
+  uint64_t* p_half = bars + 3 + 2 * ATT_SLOTS;    // [tile][key half]: P columns of 64 keys stored
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7 + 2 * ATT_SLOTS);
+  uint32_t* redo_flag = tmem_ptr + 1;  // kMode 2: some row sum left the fp32 range, repeat in the exact mode
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -106,242 +137,362 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     mbar_init(q_full, 1);
     for (int i = 0; i < ATT_SLOTS; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], kCluster ? 2 : 1);  // cluster: the slot is rewritten in both CTAs, both consumers release it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);   // one elected arrive per softmax warp
-      mbar_init(&pv_done[i], 1);
+      mbar_init(&p_half[2 * i], 4);      // one elected arrive per softmax warp
+      mbar_init(&p_half[2 * i + 1], 4);
     }
-    mbar_init(s_free, 4);
+    *redo_flag = 0u;
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(tmem_ptr, 512);
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCluster) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t crank = kCluster ? cluster_ctarank() : 0u;
 
-  // register budget: the data-movement warpgroup gives its registers to the two softmax warpgroups
-  // register budget: the data-movement warpgroup (warps 8-11) hands registers to the softmax warpgroups.
-  // The pool is what the CTA was launched with (384 x 168): 256 x 208 + 128 x 72 <= 64512.
-  if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
-    if (warp == 8 && lane == 0) {
+  // Pipeline state of every role lives outside the pass loop: kMode 2 may run the KV sweep a second time.
+  uint32_t slot = 0, phase = 0;  // KV ring position (TMA warp: producer side, MMA warp: consumer side)
+  uint32_t pph = 0;              // MMA warp: parity of the p_half barriers
+  uint32_t sphase = 0;           // softmax warps: parity of s_full
+  int pass = 0;
+  for (;;) {
+  const bool exact = kMode != 2 || pass == 1;
+  if (warp == 8) {
+    if (lane == 0) {
       // ===== TMA producer =====
-      mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+      if (pass == 0) {
+        mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
 #pragma unroll
-      for (int t = 0; t < 2; ++t)
+        for (int t = 0; t < 2; ++t)
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-          tma_load_2d(smem_q + t * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmQ, q_full,
-                      head * 128 + h * 64, q0 + t * ATT_TILE);
-      uint32_t slot = 0, phase = 0;
-      auto load_k = [&](int j) {
-        mbar_wait(&kv_empty[slot], phase ^ 1);
-        mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-          tma_load_2d(smem_kv + slot * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmK, &kv_full[slot],
-                      head * 128 + h * 64, j * ATT_TILE);
-        if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; }
-      };
-      auto load_v = [&](int j) {  // transposed: rows = head dim, columns = keys
-        mbar_wait(&kv_empty[slot], phase ^ 1);
-        mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
-        const int kv0 = j * ATT_TILE;
-        const int chunk = kv0 / p.vt_chunk_len;
-        const int koff = kv0 - chunk * p.vt_chunk_len;
-#pragma unroll
-        for (int h = 0; h < 2; ++h)
-          tma_load_3d(smem_kv + slot * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmV, &kv_full[slot],
-                      koff + h * 64, head * 128, chunk);
-        if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; }
-      };
-      // consumption order of the MMA warp: K0, then per step j: K_{j+1}, V_j
-      load_k(0);
-      for (int j = 0; j < n_kv; ++j) {
-        if (j + 1 < n_kv) load_k(j + 1);
-        load_v(j);
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d(smem_q + t * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmQ, q_full,
+                        head * 128 + h * 64, q0 + t * ATT_TILE);
       }
-    } else if (warp == 9 && lane == 0) {
+      const int tiles_per_chunk = p.vt_chunk_len / ATT_TILE;
+      const int n_chunks = p.Lk / p.vt_chunk_len;
+      for (int j = 0; j < n_kv; ++j) {
+        // KV tiles are visited chunk by chunk starting with `first_chunk` (the local one under context
+        // parallelism); a remote chunk is only touched after its producer rank has published it.
+        int chunk = p.first_chunk + j / tiles_per_chunk;
+        if (chunk >= n_chunks) chunk -= n_chunks;
+        const int within = j % tiles_per_chunk;
+        if (p.chunk_flags && within == 0 && chunk != p.first_chunk) {  // the local chunk is ordered by the stream
+          uint32_t v, spins = 0;
+          uint64_t t0 = 0;
+          for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p.chunk_flags + chunk) : "memory");
+            if ((int)(v - p.flag_seq) >= 0) break;
+            if ((++spins & 0x3FFu) == 0) {
+              const uint64_t now = global_timer_ns();
+              if (t0 == 0) t0 = now;
+              else if (now - t0 > G3C_MBAR_TIMEOUT_NS) asm volatile("trap;\n");
+            }
+          }
+          asm volatile("fence.proxy.async.global;\n" ::: "memory");  // peer-written data is read by the TMA next
+        }
+        const int kv0 = chunk * p.vt_chunk_len + within * ATT_TILE;
+        // K_j
+        mbar_wait(&kv_empty[slot], phase ^ 1);
+        mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
+        if constexpr (kCluster) {
+          tma_load_2d_mc(smem_kv + slot * ATT_TILE_BYTES + crank * ATT_HALF_BYTES, &tmK, &kv_full[slot],
+                         head * 128 + crank * 64, kv0, 3);
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d(smem_kv + slot * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmK, &kv_full[slot],
+                        head * 128 + h * 64, kv0);
+        }
+        if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; }
+        // V_j  (transposed: rows = head dim, columns = keys)
+        mbar_wait(&kv_empty[slot], phase ^ 1);
+        mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
+        const int koff = within * ATT_TILE;
+        if constexpr (kCluster) {
+          tma_load_3d_mc(smem_kv + slot * ATT_TILE_BYTES + crank * ATT_HALF_BYTES, &tmV, &kv_full[slot],
+                         koff + crank * 64, head * 128, chunk, 3);
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            tma_load_3d(smem_kv + slot * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmV, &kv_full[slot],
+                        koff + h * 64, head * 128, chunk);
+        }
+        if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
       // ===== MMA issuer =====
       constexpr uint32_t idesc = make_idesc_bf16(128, 128);
-      const uint32_t tS = tmem_base;
-      const uint32_t tP[2] = {tmem_base + 128, tmem_base + 192};
+      const uint32_t tS[2] = {tmem_base, tmem_base + 128};
       const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
-      uint32_t slot = 0, phase = 0;
-      auto take = [&]() {  // next ring slot, once the TMA has filled it
-        mbar_wait(&kv_full[slot], phase);
-        const uint32_t sl = slot;
-        if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; }
-        return sl;
-      };
-      uint32_t n_free = 0;  // how many hand-backs of the S buffer have been consumed
-      auto wait_s_free = [&]() {
-        mbar_wait(s_free, n_free & 1);
-        ++n_free;
-        tc_fence_after();
+      auto advance = [&]() { if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; } };
+      auto release_slot = [&](uint32_t sl) {
+        if constexpr (kCluster) umma_commit_mc(&kv_empty[sl], 3);
+        else umma_commit(&kv_empty[sl]);
       };
       auto mma_s = [&](int t, uint32_t kslot) {
-        // S = Q_t K^T : 8 k-steps over the head dimension
+        // S_t = Q_t K^T : 8 k-steps over the head dimension
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t half = k >> 2, off = (k & 3) * 32;
           uint64_t da = make_sdesc_sw128(smem_u32(smem_q + t * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
           uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + kslot * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
-          umma_ss(tS, sdesc_advance(da, off), sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
+          umma_ss(tS[t], sdesc_advance(da, off), sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
         }
-        umma_commit(&s_full[t]);
       };
-      auto mma_pv = [&](int t, uint32_t vslot, bool first) {
-        // O_t += P_t V : 8 k-steps over the 128 keys; A = P from TMEM (bf16 pairs per column)
+      auto mma_pv = [&](int t, uint32_t vslot, bool first, int hh) {
+        // O_t += P_t V for the 64 keys of half hh: 4 k-steps; A = P from TMEM (bf16 pairs per column)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = hh * 4 + kk;
           const uint32_t half = k >> 2, off = (k & 3) * 32;
           uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + vslot * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
-          umma_ts(tO[t], tP[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
+          umma_ts(tO[t], tS[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
         }
-        umma_commit(&pv_done[t]);
       };
-      mbar_wait(q_full, 0);
-      uint32_t kslot = take();  // K_0
+      if (pass == 0) mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[slot], phase);
       tc_fence_after();
+      uint32_t kslot = slot;
+      advance();
       mma_s(0, kslot);
-      wait_s_free();  // tile A copied S(0) out
+      umma_commit(&s_full[0]);
       mma_s(1, kslot);
-      umma_commit(&kv_empty[kslot]);
+      umma_commit(&s_full[1]);
+      release_slot(kslot);
       for (int j = 0; j < n_kv; ++j) {
         const bool more = j + 1 < n_kv;
+        mbar_wait(&kv_full[slot], phase);  // V_j
+        const uint32_t vslot = slot;
+        advance();
+        // ---- tile A
         ATT_TR(0, 0);
+        // the P·V MMAs of the first 64 keys start while the softmax still exponentiates the second 64
+        mbar_wait(&p_half[0], pph);
+        ATT_TR(0, 1);
+        tc_fence_after();
+        mma_pv(0, vslot, j == 0, 0);
+        mbar_wait(&p_half[1], pph);
+        tc_fence_after();
+        mma_pv(0, vslot, j == 0, 1);
         if (more) {
-          kslot = take();   // K_{j+1}
-          wait_s_free();    // tile B copied S_B(j) out
-          ATT_TR(0, 1);
-          mma_s(0, kslot);  // S_A(j+1): ready long before softmax A finishes tile j
-          ATT_TR(0, 2);
+          mbar_wait(&kv_full[slot], phase);  // K_{j+1}
+          tc_fence_after();
+          kslot = slot;
+          advance();
+          mma_s(0, kslot);
         }
-        const uint32_t vslot = take();  // V_j
-        mbar_wait(&p_full[0], j & 1);
+        umma_commit(&s_full[0]);
+        ATT_TR(0, 2);
+        // ---- tile B
+        mbar_wait(&p_half[2], pph);
         ATT_TR(0, 3);
         tc_fence_after();
-        mma_pv(0, vslot, j == 0);
-        ATT_TR(0, 4);
-        if (more) {
-          wait_s_free();  // tile A copied S_A(j+1) out
-          ATT_TR(0, 5);
-          mma_s(1, kslot);
-          umma_commit(&kv_empty[kslot]);
-          ATT_TR(0, 6);
-        }
-        mbar_wait(&p_full[1], j & 1);
-        ATT_TR(0, 7);
+        mma_pv(1, vslot, j == 0, 0);
+        mbar_wait(&p_half[3], pph);
         tc_fence_after();
-        mma_pv(1, vslot, j == 0);
-        umma_commit(&kv_empty[vslot]);
+        mma_pv(1, vslot, j == 0, 1);
+        release_slot(vslot);
+        if (more) {
+          mma_s(1, kslot);
+          umma_commit(&s_full[1]);
+          release_slot(kslot);
+        } else {
+          umma_commit(&s_full[1]);
+        }
+        pph ^= 1;
+        ATT_TR(0, 4);
       }
     }
-    // no code is shared after the role split (ptxas sizes each setmaxnreg region separately only then)
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 9) {
-      tc_fence_after();
-      tmem_dealloc(tmem_base, 512);
-    }
-    return;
   } else {
     // ===== softmax warpgroups (warps 0-3: tile A, warps 4-7: tile B) =====
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;\n");
     const int t = warp >> 2;
     const uint32_t lane_base = ((warp & 3u) * 32u) << 16;
-    const uint32_t tS = tmem_base + lane_base;
-    const uint32_t tP = tmem_base + lane_base + 128 + t * 64;
+    const uint32_t tS = tmem_base + lane_base + t * 128;
     const uint32_t tO = tmem_base + lane_base + 256 + t * 128;
     const float c = p.scale_log2;
-    float m_used = 0.0f;  // reference max (raw score units) the stored exponentials are relative to
-    float l = 0.0f;       // running row sum (relative to m_used)
-    const bool tr = kTrace && (warp & 3) == 0 && lane == 0;
-    for (int j = 0; j < n_kv; ++j) {
+    float ref = 0.0f;   // reference exponent (log2 units): the stored exponentials are 2^(s*c - ref)
+    float l = 0.0f;     // running row sum (relative to ref)
+    bool ovf = false;   // kMode 2: the running row sum left the safe range at some tile
+    bool plain = false; // kMode 2: ref == 0 in every row of this warp and S is in log2 units
+    float pend = 0.0f;  // kMode 2: exponent shift to apply to ref / O / l before the next tile (0 = none)
+    const bool tr = kTrace == 1 && (warp & 3) == 0 && lane == 0;
+    auto rescale = [&](float alpha) {
+      // s_full(j) was committed after PV(j-1): O already holds every earlier contribution.
+      l *= alpha;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t o[32];
+        tmem_ld32(tO + cc * 32, o);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st32(tO + cc * 32, o);
+      }
+      tc_wait_st();
+    };
+    // exponentials of 64 keys (S values in sv) -> bf16 pairs in pk, partial row sums in ls
+    auto exp64 = [&](const uint32_t* sv, float neg, uint32_t* pk, float* ls) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float xa = fmaf(__uint_as_float(sv[2 * i]), c, neg);
+        const float xb = fmaf(__uint_as_float(sv[2 * i + 1]), c, neg);
+        const float a = ex2_approx(xa);
+        const float b = (kPolyEvery > 0 && (i % (kPolyEvery / 2 > 0 ? kPolyEvery / 2 : 1)) == 0) ? ex2_poly(xb) : ex2_approx(xb);
+        ls[(2 * i) & 3] += a;
+        ls[(2 * i + 1) & 3] += b;
+        pk[i] = pack_bf16x2(a, b);
+      }
+    };
+    // P columns of half hh are in TMEM: make them visible to the tensor pipe and tell the MMA warp
+    auto release_half = [&](int hh) {
+      if (p.p_halves || hh == 1) {
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (!p.p_halves) mbar_arrive(&p_half[2 * t]);
+          mbar_arrive(&p_half[2 * t + hh]);
+        }
+      }
+    };
+    auto wait_s = [&](int j) {
       if (tr) ATT_TR(1 + t, 0);
-      mbar_wait(&s_full[t], j & 1);
+      mbar_wait(&s_full[t], sphase);
       if (tr) ATT_TR(1 + t, 1);
+      sphase ^= 1;
       tc_fence_after();
+    };
+    // exact tile: whole S row in registers, row max, lazy rescale, exponentials
+    auto tile_exact = [&](int j) {
+      wait_s(j);
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t s[128];
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) tmem_ld32(tS + cc * 32, s + cc * 32);
       tc_wait_ld();
       if (tr) ATT_TR(1 + t, 2);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_free);  // the score buffer may be overwritten by the next QK
-      // 8 independent max chains (a single dependent FMNMX chain costs ~6 clk per link: 400 clk per tile
-      // in the round-1 profile)
+      // 8 independent max chains (a single dependent FMNMX chain costs ~6 clk per link)
       float mxs[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) mxs[i] = __uint_as_float(s[i]);
 #pragma unroll
       for (int i = 8; i < 128; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], __uint_as_float(s[i]));
-      const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
-                             fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+      const float mxl = c * fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                                  fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
       if (j == 0) {
-        m_used = mx;
-      } else {
-        const bool grow = (mx - m_used) * c > 8.0f;
-        if (__any_sync(0xffffffffu, grow)) {
-          // O must hold every earlier contribution before it is rescaled: wait for PV(j-1)
-          mbar_wait(&pv_done[t], (j - 1) & 1);
-          tc_fence_after();
-          const float m_new = fmaxf(m_used, mx);
-          const float alpha = ex2_approx((m_used - m_new) * c);
-          m_used = m_new;
-          l *= alpha;
-#pragma unroll 1
-          for (int cc = 0; cc < 4; ++cc) {
-            uint32_t o[32];
-            tmem_ld32(tO + cc * 32, o);
-            tc_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tO + cc * 32, o);
-          }
-          tc_wait_st();
-        }
+        // kMode 2 with S already in log2 units: if every first-tile row max of this warp is within 2^+-40 the
+        // reference stays 0 and the fast tiles need no subtraction at all (p = 2^s)
+        plain = !exact && p.unit_scale && __all_sync(0xffffffffu, fabsf(mxl) <= 40.0f);
+        ref = plain ? 0.0f : mxl;
+      } else if (__any_sync(0xffffffffu, mxl - ref > 8.0f)) {  // lazy: only when the max grew by > 2^8
+        const float nref = fmaxf(ref, mxl);
+        rescale(ex2_approx(ref - nref));
+        ref = nref;
       }
-      const float neg = -m_used * c;
       if (tr) ATT_TR(1 + t, 3);
-      float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float xa = fmaf(__uint_as_float(s[hh * 64 + 2 * i]), c, neg);
-          const float xb = fmaf(__uint_as_float(s[hh * 64 + 2 * i + 1]), c, neg);
-          float a = ex2_approx(xa);
-          float b = (kPolyEvery > 0 && (i % (kPolyEvery / 2 > 0 ? kPolyEvery / 2 : 1)) == 0) ? ex2_poly(xb) : ex2_approx(xb);
-          ls[(2 * i) & 3] += a;
-          ls[(2 * i + 1) & 3] += b;
-          pk[i] = pack_bf16x2(a, b);
-        }
-        if (hh == 0 && j > 0) {
-          // P_t is still the A operand of PV(j-1) until that MMA has committed (normally long ago)
-          mbar_wait(&pv_done[t], (j - 1) & 1);
-          tc_fence_after();
-        }
-        tmem_st32(tP + hh * 32, pk);
+        exp64(s + hh * 64, -ref, pk, ls);
+        tmem_st32(tS + hh * 32, pk);
+        release_half(hh);
         if (tr && hh == 0) ATT_TR(1 + t, 4);
       }
       l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-      tc_wait_st();
       if (tr) ATT_TR(1 + t, 5);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[t]);
       if (tr) ATT_TR(1 + t, 6);
+    };
+    // fast tile (kMode 2, j > 0): no row max; S is read 64 columns at a time so that only half a row is live.
+    // Row sums exceeding kBig shift the reference before the next tile (see the kMode comment).
+    auto fast_tail = [&](float tsum, int j) {
+      l += tsum;
+      // sticky: O <= l * max|v|, so a running sum that stays below 2^90 keeps O finite as well; a transient excursion
+      // (later scaled away by a shift) would otherwise leave inf in O behind a harmless-looking final l
+      ovf |= !(l < 1e27f);
+      // inf: exponent field 255 -> shift 100, l is non-finite by then and the CTA takes the exact second pass
+      const int e = ((__float_as_int(tsum) >> 23) & 0xff) - 127;
+      pend = tsum > 1.0995116e12f /* 2^40 */ ? (float)(e < 100 ? e : 100) : 0.0f;
+      if (tr) ATT_TR(1 + t, 5);
+      if (tr) ATT_TR(1 + t, 6);
+    };
+    auto tile_fast = [&](int j) {
+      wait_s(j);
+      if (__any_sync(0xffffffffu, pend != 0.0f)) {
+        rescale(__int_as_float((127 - (int)pend) << 23));  // exact power of two
+        ref += pend;
+        pend = 0.0f;
+        plain = false;
+      }
+      uint32_t s[64], pk[32];
+      tmem_ld32(tS, s);
+      tmem_ld32(tS + 32, s + 32);
+      tc_wait_ld();
+      if (tr) ATT_TR(1 + t, 2);
+      if (tr) ATT_TR(1 + t, 3);
+      if (plain) {
+        // p = 2^s: one MUFU per element, one FADD2 and one F2FP per pair
+        uint64_t ls2[2] = {0ull, 0ull};
+        auto exp64p = [&]() {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float a = ex2_approx(__uint_as_float(s[2 * i])), b = ex2_approx(__uint_as_float(s[2 * i + 1]));
+            ls2[i & 1] = fadd2(ls2[i & 1], pack2(a, b));
+            pk[i] = pack_bf16x2(a, b);
+          }
+        };
+        exp64p();
+        tmem_st32(tS, pk);
+        tmem_ld32(tS + 64, s);  // second half of the row arrives under the release of the first P half
+        tmem_ld32(tS + 96, s + 32);
+        release_half(0);
+        if (tr) ATT_TR(1 + t, 4);
+        tc_wait_ld();
+        exp64p();
+        tmem_st32(tS + 32, pk);
+        release_half(1);
+        float s0, s1, s2, s3;
+        unpack2(ls2[0], s0, s1);
+        unpack2(ls2[1], s2, s3);
+        fast_tail((s0 + s1) + (s2 + s3), j);
+      } else {
+        const float neg = -ref;
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
+        exp64(s, neg, pk, ls);
+        tmem_st32(tS, pk);
+        tmem_ld32(tS + 64, s);
+        tmem_ld32(tS + 96, s + 32);
+        release_half(0);
+        if (tr) ATT_TR(1 + t, 4);
+        tc_wait_ld();
+        exp64(s, neg, pk, ls);
+        tmem_st32(tS + 32, pk);
+        release_half(1);
+        fast_tail((ls[0] + ls[1]) + (ls[2] + ls[3]), j);
+      }
+    };
+    if (exact) {
+#pragma unroll 1
+      for (int j = 0; j < n_kv; ++j) tile_exact(j);
+    } else {
+      tile_exact(0);
+#pragma unroll 1
+      for (int j = 1; j < n_kv; ++j) tile_fast(j);
     }
     // final: PV(n_kv-1) complete
-    mbar_wait(&pv_done[t], (n_kv - 1) & 1);
+    mbar_wait(&s_full[t], sphase);
+    sphase ^= 1;
     tc_fence_after();
+    if constexpr (kMode == 2) {
+      if (pass == 0 && (ovf || !(l < 1e27f))) *reinterpret_cast<volatile uint32_t*>(redo_flag) = 1u;
+    }
     const int row = q0 + t * ATT_TILE + (warp & 3) * 32 + lane;
     const float inv = 1.0f / l;
     __nv_bfloat16* optr = p.O + (size_t)row * p.ldo + head * 128;
@@ -362,27 +513,38 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         }
       }
     }
-    tc_fence_before();
-    __syncthreads();
+  }
+    if constexpr (kMode != 2) {
+      break;
+    } else {
+      // did any row of this CTA leave the fp32 range?  (never for RMS-normalised q/k; the generic kernel must cope)
+      tc_fence_before();
+      __syncthreads();
+      if constexpr (kCluster) {
+        // both CTAs of a cluster share the K / V ring protocol: they repeat the sweep together or not at all
+        if (threadIdx.x == 0 && pass == 0 && *reinterpret_cast<volatile uint32_t*>(redo_flag) != 0u)
+          st_shared_cluster_u32(redo_flag, crank ^ 1u, 1u);
+        cluster_sync_all();
+      }
+      tc_fence_after();
+      if (pass == 1 || *reinterpret_cast<volatile uint32_t*>(redo_flag) == 0u) break;
+      pass = 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (kCluster) cluster_sync_all();  // no arrive / multicast may target a CTA that has already exited
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
-namespace v1 {
-extern unsigned long long* g_attn_trace;
-int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, int Lk, int heads, int ldq,
-                int ldk, int ldo, int vt_chunk_len, float scale, cudaStream_t st, const ChunkGate* gate);
-}
+unsigned long long* g_attn_trace = nullptr;  // set through g3c_attn_set_trace (profiling aid, not a product path)
 
-int attn_fwd(const void* q, const void* k, const void* vt, void* o, int Lq, int Lk, int heads,
-             int ldq, int ldk, int ldo, int vt_chunk_len, float scale, cudaStream_t st, const ChunkGate* gate) {
-  // Default: the round-1 baseline kernel (attn_tcgen05_v1.cu), which measured 3-6 % faster on B200 than this
-  // decoupled-issue kernel (profiles/r01_attention_variants.txt).  G3C_ATTN_IMPL=v4 selects this one.
-  static int use_v1 = -1;
-  if (use_v1 < 0) {
-    const char* e = getenv("G3C_ATTN_IMPL");
-    use_v1 = (e && e[0] == 'v' && e[1] == '4') ? 0 : 1;
-  }
-  if (use_v1 || gate) return v1::attn_fwd_v1(q, k, vt, o, Lq, Lk, heads, ldq, ldk, ldo, vt_chunk_len, scale, st, gate);
+int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, int Lk, int heads,
+                int ldq, int ldk, int ldo, int vt_chunk_len, float scale, cudaStream_t st, const ChunkGate* gate) {
   G3C_REQUIRE(q && k && vt && o, "attn: null operand");
   G3C_REQUIRE(Lq > 0 && Lk > 0 && heads > 0, "attn: bad sizes");
   G3C_REQUIRE(Lk % ATT_TILE == 0, "attn: Lk=%d must be a multiple of 128", Lk);
@@ -414,17 +576,23 @@ int attn_fwd(const void* q, const void* k, const void* vt, void* o, int Lq, int 
     int rc = make_tmap_bf16_sw128(&tmV, vt, 3, dims, str, box);
     if (rc) return rc;
   }
-  // fraction of exponentials evaluated on the FMA pipe: 1/kPolyEvery (0 = none); G3C_ATTN_POLY overrides
-  static int poly = -1;
+  // G3C_ATTN_MODE: softmax variant (see k_attn_fwd), 2 = sum-guarded reference (default), 0 = exact max per tile;
+  // G3C_ATTN_POLY=4: every 4th exponential on the FMA pipe (measured slower, kept for A/B runs)
+  static int poly = -1, mode = 2, cluster = 1;
   if (poly < 0) {
     const char* e = getenv("G3C_ATTN_POLY");
-    poly = e ? atoi(e) : 0;
-    if (poly != 0 && poly != 2 && poly != 4 && poly != 8) poly = 4;
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    poly = (e && atoi(e) != 0) ? 4 : 0;
+    e = getenv("G3C_ATTN_MODE");
+    mode = e ? (atoi(e) != 0 ? 2 : 0) : 2;
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 0, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<4, 0, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 1, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 1, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    e = getenv("G3C_ATTN_CLUSTER");
+    cluster = e ? atoi(e) != 0 : 1;
   }
   AttnParams p;
   p.Lq = Lq;
@@ -434,20 +602,69 @@ int attn_fwd(const void* q, const void* k, const void* vt, void* o, int Lq, int 
   p.vt_chunk_len = vt_chunk_len;
   p.O = reinterpret_cast<__nv_bfloat16*>(o);
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.unit_scale = fabsf(p.scale_log2 - 1.0f) < 1e-6f;  // scale = ln 2: the caller already folded scale * log2(e) into Q
+  if (p.unit_scale) p.scale_log2 = 1.0f;
   dim3 grid((Lq + 2 * ATT_TILE - 1) / (2 * ATT_TILE), heads);
-  p.trace = v1::g_attn_trace;
-  if (p.trace) {
-    k_attn_fwd<0, true><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+  p.chunk_flags = gate ? gate->flags : nullptr;
+  p.flag_seq = gate ? gate->seq : 0;
+  p.first_chunk = gate ? gate->first : 0;
+  static int halves = -1;
+  if (halves < 0) {
+    const char* e = getenv("G3C_ATTN_PHALF");
+    halves = e ? (atoi(e) != 0) : 1;
+  }
+  p.p_halves = halves;
+  G3C_REQUIRE(p.first_chunk >= 0 && p.first_chunk < Lk / vt_chunk_len, "attn: first chunk %d out of range", p.first_chunk);
+  p.trace = g_attn_trace;
+  if (g_attn_trace) {
+    const char* mo = getenv("G3C_ATTN_TRACE_MMA_ONLY");  // stamps of the MMA warp only: no perturbation of the softmax warps
+    if (mode && mo && atoi(mo)) k_attn_fwd<0, 2, 2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+    else if (mode) k_attn_fwd<0, 1, 2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+    else k_attn_fwd<0, 1, 0, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+  } else if (mode == 0 || Lk <= 8 * ATT_TILE) {
+    // also the choice for short key ranges (cross-attention: 4 KV tiles): the CTA is prologue-bound there and the
+    // cluster launch / second-pass agreement of the default path only add latency (0.72 vs 0.83 ms at 56 320 x 512)
+    k_attn_fwd<0, 0, 0, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+  } else if (poly) {
+    k_attn_fwd<4, 0, 2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
+  } else if (cluster && (grid.x % 2 == 0 || grid.x < 16)) {
+    // CTA pairs along the query dimension sharing every K / V tile through TMA multicast.  An odd number of query
+    // blocks would need a padding CTA (zero-filled Q rows, stores nothing): worth it only for small grids, where it
+    // keeps this path covered by the unit tests; e.g. 55 blocks at cp = 4 run unpaired instead.
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((grid.x + 1) & ~1u, grid.y);
+    cfg.blockDim = dim3(ATT_THREADS);
+    cfg.dynamicSmemBytes = ATT_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 0, 2, true>, tmQ, tmK, tmV, p));
   } else {
-    switch (poly) {
-      case 0: k_attn_fwd<0, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-      case 2: k_attn_fwd<2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-      case 8: k_attn_fwd<8, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-      default: k_attn_fwd<4, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p); break;
-    }
+    k_attn_fwd<0, 0, 2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
   }
   G3C_CUDA(cudaGetLastError());
   return G3C_OK;
+}
+
+}  // namespace v1
+}  // namespace g3c
+
+extern "C" int g3c_attn_set_trace(unsigned long long* device_buffer) {
+  g3c::v1::g_attn_trace = device_buffer;
+  return G3C_OK;
+}
+
+namespace g3c {
+
+// Host entry used by the engine and by the C ABI.
+int attn_fwd(const void* q, const void* k, const void* vt, void* o, int Lq, int Lk, int heads,
+             int ldq, int ldk, int ldo, int vt_chunk_len, float scale, cudaStream_t st, const ChunkGate* gate) {
+  return v1::attn_fwd_v1(q, k, vt, o, Lq, Lk, heads, ldq, ldk, ldo, vt_chunk_len, scale, st, gate);
 }
 
 }  // namespace g3c

@@ -1,4 +1,4 @@
-"""Per-phase clock64 timeline of one attention CTA (profiling aid; honours G3C_ATTN_IMPL=v1|v5)."""
+"""Per-phase clock64 timeline of one attention CTA (profiling aid; G3C_ATTN_MODE=0|2, G3C_ATTN_TRACE_MMA_ONLY=1)."""
 import sys
 
 import torch
