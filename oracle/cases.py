@@ -71,6 +71,20 @@ def warp_case(name: str):
     raise KeyError(name)
 
 
+def foreground_case():
+    """R7: a near box (1.2 m) in front of a smooth background (2.9 - 4.1 m), camera yawed and
+    shifted so that the box edge occludes background pixels.  boundary mask = depth-discontinuity pixels."""
+    rng = np.random.RandomState(7)
+    h, w = 96, 128
+    depth = (2.9 + 0.35 * smooth_depth(h, w)).astype(F32)
+    depth[30:70, 44:84] = 1.2 + 0.02 * smooth_depth(h, w)[30:70, 44:84]
+    img = rng.uniform(-1, 1, (1, 3, h, w)).astype(F32)
+    K = intrinsics(h, w, 100.0)
+    eye = np.eye(4, dtype=F32)
+    return dict(depth=depth[None, None], image=img, mask=None, w2c_src=eye[None], K=K[None],
+                w2c_tgt=look(0.06, -0.015, (0.12, 0.01, 0.03))[None])
+
+
 def look(yaw: float, pitch: float, t) -> np.ndarray:
     """world-to-camera matrix: rotation yaw (about y) then pitch (about x), translation t."""
     cy, sy, cp, sp = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch)

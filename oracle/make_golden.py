@@ -87,7 +87,59 @@ def mint_warp():
     if bad or e_cache > 2e-3:
         print("!! restated warp oracle disagrees with the reference:", bad, e_cache)
         return 1
-    return 0
+    return mint_foreground(ref)
+
+
+def torch_ray_triangle(ray_origins, ray_directions, vertices, faces, device):
+    """Stand-in for the NVIDIA Warp kernel (ray_triangle_intersection_warp.py:23-105, launched at :243-258 / :267-287),
+    which needs Warp + CUDA: the same Moeller-Trumbore test, brute force in float32 torch.  Everything else on the
+    foreground-masking path below is the reference's own code."""
+    H, W = ray_origins.shape[:2]
+    o, d = ray_origins.reshape(-1, 1, 3).float(), ray_directions.reshape(-1, 1, 3).float()
+    v0, v1, v2 = vertices[faces[:, 0]][None], vertices[faces[:, 1]][None], vertices[faces[:, 2]][None]
+    e1, e2 = v1 - v0, v2 - v0
+    h = torch.cross(d.expand(-1, e2.shape[1], -1), e2.expand(d.shape[0], -1, -1), dim=-1)
+    a = (e1 * h).sum(-1)
+    ok = a.abs() >= 1e-8
+    f = 1.0 / a
+    s = o - v0
+    u = f * (s * h).sum(-1)
+    ok &= ~((u < 0) | (u > 1))
+    q = torch.cross(s, e1.expand(s.shape[0], -1, -1), dim=-1)
+    v = f * (d * q).sum(-1)
+    ok &= ~((v < 0) | (u + v > 1))
+    tt = f * (e2 * q).sum(-1)
+    ok &= tt > 1e-8
+    tt = torch.where(ok, tt, torch.full_like(tt, 1e10))
+    best = tt.min(dim=1).values
+    return torch.where(best < 1e10, best, torch.zeros_like(best)).reshape(H, W)
+
+
+def mint_foreground(ref):
+    """forward_warp(foreground_masking=True) of the reference on CPU (R7) -> tests/golden/warp_R7_foreground.npz."""
+    ref._warp_initialized = True
+    ref._ray_triangle_intersection_func = torch_ray_triangle
+    c = cases.foreground_case()
+    with torch.no_grad():
+        pts = ref.unproject_points(t(c["depth"]), t(c["w2c_src"]), t(c["K"]), is_depth=True)
+        boundary = ~ref.reliable_depth_mask_range_batch(t(c["depth"]))[:, 0]
+        base = ref.forward_warp(t(c["image"]), None, None, None, t(c["w2c_tgt"]), t(c["K"]), t(c["K"]), render_depth=True,
+                                world_points1=pts)
+        warped, mask, depth, flow = ref.forward_warp(t(c["image"]), None, None, None, t(c["w2c_tgt"]), t(c["K"]), t(c["K"]),
+                                                     world_points1=pts, foreground_masking=True, boundary_mask=boundary)
+    b_o = ~(warp_oracle.reliable_depth_mask_range_batch(c["depth"]).astype(bool)[:, 0])
+    w_o, m_o, d_o, _ = warp_oracle.forward_warp(c["image"], None, pts.numpy(), c["w2c_tgt"], c["K"], foreground_masking=True,
+                                                boundary_mask=b_o)
+    killed = float(((base[1] > 0) & (mask == 0)).float().mean())
+    flips = float((m_o != mask.numpy()).mean())
+    same = (m_o == mask.numpy())[:, 0]
+    e_img = float(np.abs(w_o - warped.numpy())[np.broadcast_to(same[:, None], w_o.shape)].max())
+    print("Path R foreground masking (R7): boundary px %.3f, occluded px %.4f, oracle mask flips %.2e, image err %.2e, "
+          "boundary mask equal: %s" % (float(boundary.float().mean()), killed, flips, e_img,
+                                       bool((b_o == boundary.numpy()).all())))
+    np.savez_compressed(os.path.join(OUT, "warp_R7_foreground.npz"), points=pts.numpy(), boundary=boundary.numpy(),
+                        warped=warped.numpy(), mask=mask.numpy(), depth=depth.numpy(), mask_plain=base[1].numpy())
+    return 0 if (killed > 0.005 and flips < 2e-3 and e_img < 2e-3) else 1
 
 
 def mint_dit():

@@ -56,12 +56,14 @@ def unproject_points(depth, w2c, intrinsic, is_depth=True, mask=None) -> np.ndar
     return out
 
 
-def project_points(world_points, w2c, intrinsic):
-    """:462-486.  world_points (b,h,w,3) -> (b,h,w,3) = K (w2c [p;1])[:3]."""
+def project_points(world_points, w2c, intrinsic, return_cam_points=False):
+    """:462-486.  world_points (b,h,w,3) -> (b,h,w,3) = K (w2c [p;1])[:3]; optionally also the camera-space points."""
     b, h, w, _ = world_points.shape
     homo = np.concatenate([world_points.astype(F32), np.ones((b, h, w, 1), dtype=F32)], axis=3)[..., None]
     cam = np.matmul(w2c.astype(F32)[:, None, None], homo)[:, :, :, :3]
     proj = np.matmul(intrinsic.astype(F32)[:, None, None], cam)
+    if return_cam_points:
+        return proj[..., 0].astype(F32), cam[..., 0].astype(F32)
     return proj[..., 0].astype(F32)
 
 
@@ -127,14 +129,15 @@ def bilinear_splatting(frame1, mask1, depth1, flow12, is_image=False, depth_weig
 
 
 def forward_warp(frame1, mask1, world_points1, transformation2, intrinsic2, is_image=True,
-                 render_depth=False):
+                 render_depth=False, foreground_masking=False, boundary_mask=None):
     """:171-336, the depth1=None / world_points1 branch (:219-224, :244-250, :281-284), without
-    normal filtering or foreground masking.  Returns (warped, mask2, depth2|None, flow12)."""
+    normal filtering; with the foreground-masking occlusion pass (:285-335) when asked.
+    Returns (warped, mask2, depth2|None, flow12)."""
     frame1 = frame1.astype(F32)
     b, c, h, w = frame1.shape
     if mask1 is None:
         mask1 = np.ones((b, 1, h, w), dtype=F32)
-    tp = project_points(world_points1, transformation2, intrinsic2)  # (b,h,w,3)
+    tp, cam_points_target = project_points(world_points1, transformation2, intrinsic2, return_cam_points=True)
     z = tp[:, :, :, 2][:, None]
     mask1 = mask1.astype(F32) * (z > 0)
     with np.errstate(divide="ignore", invalid="ignore"):
@@ -143,9 +146,121 @@ def forward_warp(frame1, mask1, world_points1, transformation2, intrinsic2, is_i
     flow12 = coords - create_grid(b, h, w)
     warped, mask2 = bilinear_splatting(frame1, mask1, z, flow12, is_image=is_image)
     depth2 = None
-    if render_depth:
+    if render_depth or foreground_masking:
         depth2 = bilinear_splatting(z, mask1, z, flow12, is_image=False)[0][:, 0]
+    if foreground_masking:
+        assert boundary_mask is not None
+        for bi in range(b):
+            closer = foreground_occlusion(cam_points_target[bi], boundary_mask[bi].astype(bool), intrinsic2[bi], depth2[bi])
+            if closer is None:
+                continue
+            keep = (~closer).astype(F32)
+            mask2[bi, 0] = mask2[bi, 0] * keep
+            warped[bi] = (warped[bi] + F32(1)) * keep[None] - F32(1)
+            depth2[bi] = depth2[bi] * keep
     return warped, mask2, depth2, flow12
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# foreground-masking occlusion pass
+# ------------------------------------------------------------------------------------------------------------------
+def _interp_axis_bilinear(n_in: int, n_out: int):
+    """Source indices / weights of F.interpolate(mode="bilinear", align_corners=False) along one axis."""
+    scale = F32(n_in) / F32(n_out)
+    src = np.maximum((np.arange(n_out, dtype=F32) + F32(0.5)) * scale - F32(0.5), F32(0))
+    i0 = np.minimum(np.floor(src).astype(np.int64), n_in - 1)
+    i1 = np.minimum(i0 + 1, n_in - 1)
+    lam = (src - i0.astype(F32)).astype(F32)
+    return i0, i1, lam
+
+
+def resize_bilinear(x: np.ndarray, new_h: int, new_w: int) -> np.ndarray:
+    """x (..., H, W) -> (..., new_h, new_w), torch's bilinear, align_corners=False (no antialias)."""
+    y0, y1, ly = _interp_axis_bilinear(x.shape[-2], new_h)
+    x0, x1, lx = _interp_axis_bilinear(x.shape[-1], new_w)
+    x = x.astype(F32)
+    top = x[..., y0, :][..., :, x0] * (F32(1) - lx) + x[..., y0, :][..., :, x1] * lx
+    bot = x[..., y1, :][..., :, x0] * (F32(1) - lx) + x[..., y1, :][..., :, x1] * lx
+    return (top * (F32(1) - ly)[:, None] + bot * ly[:, None]).astype(F32)
+
+
+def resize_nearest(x: np.ndarray, new_h: int, new_w: int) -> np.ndarray:
+    """torch's mode="nearest": source index floor(dst * in / out)."""
+    yi = np.minimum(np.floor(np.arange(new_h, dtype=F32) * (F32(x.shape[-2]) / F32(new_h))).astype(np.int64), x.shape[-2] - 1)
+    xi = np.minimum(np.floor(np.arange(new_w, dtype=F32) * (F32(x.shape[-1]) / F32(new_w))).astype(np.int64), x.shape[-1] - 1)
+    return x[..., yi, :][..., :, xi]
+
+
+def points_to_mesh(points: np.ndarray, mask: np.ndarray, resolution=None):
+    """forward_warp_utils_pytorch.py:49-132.  points (H,W,3), mask (H,W) bool -> (vertices (H'*W',3), faces (M,3) int64).
+    The reference additionally drops unused vertices and renumbers the faces; that relabelling does not change any
+    triangle, so the vertex grid is kept whole here."""
+    if resolution is not None:
+        nh, nw = resolution
+        points = np.moveaxis(resize_bilinear(np.moveaxis(points.astype(F32), 2, 0), nh, nw), 0, 2)
+        mask = resize_nearest(mask.astype(F32), nh, nw) != 0
+    H, W = mask.shape
+    idx = np.arange(H * W).reshape(H, W)
+    valid = mask[:-1, :-1] | mask[:-1, 1:] | mask[1:, :-1] | mask[1:, 1:]
+    vh, vw = np.nonzero(valid)
+    tl, tr, bl, br = idx[vh, vw], idx[vh, vw + 1], idx[vh + 1, vw], idx[vh + 1, vw + 1]
+    faces = np.concatenate([np.stack([tl, tr, bl], 1), np.stack([tr, br, bl], 1)], 0)
+    return points.reshape(-1, 3).astype(F32), faces
+
+
+def get_camera_rays(h: int, w: int, intrinsic: np.ndarray) -> np.ndarray:
+    """:151-168.  intrinsic (3,3) -> unit rays (h,w,3) through the pixel centres' integer coordinates."""
+    kinv = inverse_with_conversion(intrinsic[None])[0]
+    xs, ys = np.meshgrid(np.arange(w, dtype=F32), np.arange(h, dtype=F32))
+    pos = np.stack([xs, ys, np.ones_like(xs)], axis=-1)[..., None]  # (h,w,3,1)
+    un = np.matmul(kinv[None, None], pos)[..., 0].astype(F32)
+    nrm = np.linalg.norm(un, axis=-1, keepdims=True).astype(F32)
+    nrm[nrm == 0] = 1
+    return (un / nrm).astype(F32)
+
+
+def ray_triangle_depth(origins: np.ndarray, dirs: np.ndarray, vertices: np.ndarray, faces: np.ndarray,
+                       eps: float = 1e-8, tri_chunk: int = 512) -> np.ndarray:
+    """Restates the NVIDIA Warp kernel ray_triangle_intersection_warp.py:23-105 (Moeller-Trumbore, nearest hit with
+    t > eps, 0 where nothing is hit) in float32.  PARITY UNPINNED for this function: the reference implementation is a
+    Warp/CUDA kernel that cannot run in the build container; everything around it is pinned (make_golden.py)."""
+    o, d = origins.reshape(-1, 3).astype(F32), dirs.reshape(-1, 3).astype(F32)
+    best = np.full(o.shape[0], F32(1e10), dtype=F32)
+    eps = F32(eps)
+    for t0 in range(0, faces.shape[0], tri_chunk):
+        f = faces[t0:t0 + tri_chunk]
+        v0, v1, v2 = vertices[f[:, 0]], vertices[f[:, 1]], vertices[f[:, 2]]
+        e1, e2 = (v1 - v0).astype(F32), (v2 - v0).astype(F32)                   # (T,3)
+        h = np.cross(d[:, None, :], e2[None, :, :]).astype(F32)                  # (R,T,3)
+        a = np.einsum("tk,rtk->rt", e1, h).astype(F32)
+        ok = np.abs(a) >= eps
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            fi = (F32(1) / a).astype(F32)
+            s = (o[:, None, :] - v0[None, :, :]).astype(F32)
+            u = (fi * np.einsum("rtk,rtk->rt", s, h)).astype(F32)
+            ok &= ~((u < 0) | (u > 1))
+            q = np.cross(s, e1[None, :, :]).astype(F32)
+            v = (fi * np.einsum("rk,rtk->rt", d, q)).astype(F32)
+            ok &= ~((v < 0) | ((u + v) > 1))
+            t = (fi * np.einsum("tk,rtk->rt", e2, q)).astype(F32)
+        ok &= t > eps
+        t = np.where(ok, t, F32(1e10))
+        best = np.minimum(best, t.min(axis=1))
+    return np.where(best < F32(1e10), best, F32(0)).astype(F32)
+
+
+def foreground_occlusion(cam_points_target, boundary_mask, intrinsic2, warped_depth2, mesh_downsample_factor=4):
+    """:285-329 for one batch item: mesh of the 1/4-resolution target-camera points around boundary pixels, nearest
+    ray/mesh hit per target pixel, `closer` = mesh in front of the splatted depth by more than 0.02.  None when the
+    mesh is empty (the reference `continue`s)."""
+    h, w = boundary_mask.shape
+    vertices, faces = points_to_mesh(cam_points_target, boundary_mask, (h // mesh_downsample_factor, w // mesh_downsample_factor))
+    if faces.shape[0] == 0:
+        return None
+    rays = get_camera_rays(h, w, intrinsic2)
+    t = ray_triangle_depth(np.zeros_like(rays), rays, vertices, faces).reshape(h, w)
+    mesh_z = resize_bilinear((t * rays[:, :, 2]).astype(F32)[None], h, w)[0]  # same size: identity resample
+    return ((mesh_z + F32(0.02)) < warped_depth2) & (mesh_z > 0)
 
 
 def reliable_depth_mask_range_batch(depth, window_size=5, ratio_thresh=0.05, eps=1e-6):

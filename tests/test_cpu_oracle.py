@@ -28,6 +28,40 @@ def test_warp_oracle_matches_reference_golden(name, golden_dir):
     assert np.array_equal(ce.astype(np.int32), g["ceil"])
 
 
+def test_foreground_masking_oracle_matches_reference_golden(golden_dir):
+    """SURVEY.md §8f rank 1 (next row): forward_warp(foreground_masking=True).  The golden comes from the reference's own
+    forward_warp / points_to_mesh / get_camera_rays run on CPU; only the NVIDIA-Warp ray/triangle kernel is replaced by
+    a torch restatement there (oracle/make_golden.py::torch_ray_triangle)."""
+    g = np.load(os.path.join(golden_dir, "warp_R7_foreground.npz"))
+    c = cases.foreground_case()
+    boundary = ~warp_oracle.reliable_depth_mask_range_batch(c["depth"]).astype(bool)[:, 0]
+    assert np.array_equal(boundary, g["boundary"])
+    w, m, d, _ = warp_oracle.forward_warp(c["image"], None, g["points"], c["w2c_tgt"], c["K"], foreground_masking=True,
+                                          boundary_mask=boundary)
+    assert np.array_equal(m, g["mask"])
+    np.testing.assert_allclose(w, g["warped"], atol=1e-4)
+    np.testing.assert_allclose(d, g["depth"], atol=1e-5)
+    occluded = (g["mask_plain"] > 0) & (g["mask"] == 0)
+    assert 0.02 < occluded.mean() < 0.06  # the near box hides a strip of background behind its edge
+    assert np.all(w[0][:, occluded[0, 0]] == -1.0)  # killed pixels carry the fill value of an image
+
+
+def test_ray_triangle_known_answers():
+    """Moeller-Trumbore restatement on hand-checkable geometry: a unit right triangle at z = 2."""
+    v = np.array([[0, 0, 2], [1, 0, 2], [0, 1, 2]], dtype=np.float32)
+    f = np.array([[0, 1, 2]])
+    d = np.array([[0.1, 0.1, 1.0], [0.6, 0.6, 1.0], [0.0, 0.0, -1.0], [0.25, 0.25, 1.0]], dtype=np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    t = warp_oracle.ray_triangle_depth(np.zeros_like(d), d, v, f)
+    np.testing.assert_allclose(t[0] * d[0, 2], 2.0, rtol=1e-6)   # inside: z-depth of the plane
+    assert t[1] == 0.0 and t[2] == 0.0                           # u + v > 1 ; behind the camera
+    np.testing.assert_allclose(t[3] * d[3, 2], 2.0, rtol=1e-6)
+    # nearest of two parallel triangles wins
+    v2 = np.concatenate([v, v + np.array([0, 0, 1], dtype=np.float32)])
+    t2 = warp_oracle.ray_triangle_depth(np.zeros_like(d), d, v2, np.array([[3, 4, 5], [0, 1, 2]]))
+    np.testing.assert_allclose(t2[0] * d[0, 2], 2.0, rtol=1e-6)
+
+
 def test_identity_camera_kat():
     """256x256, identity camera, smooth depth -> image reproduced, mask all ones."""
     c = cases.warp_case("R1")
