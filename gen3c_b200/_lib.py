@@ -76,6 +76,7 @@ SIGNATURES = {
     "g3c_splat_indices": (_I, [_P, _I, _I, _I, _P, _P]),
     "g3c_unproject_points": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "g3c_reliable_depth_mask": (_I, [_P, _I, _I, _I, _I, _F, _F, _P, _P]),
+    "g3c_foreground_occlusion": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
     "g3c_gemm_bf16": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
     "g3c_gemm_norm_rope_bf16": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _F, _P]),
     "g3c_attn_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P]),

@@ -395,6 +395,183 @@ struct g3c_render {
   int gmax_cap;
 };
 
+
+// ------------------------------------------------------------------------------------------------
+// Foreground-masking occlusion pass (reference forward_warp :285-335, points_to_mesh :49-132,
+// get_camera_rays :151-168, NVIDIA-Warp kernel ray_triangle_intersection_warp.py:23-105).
+// The reference ray-traces every target pixel against every triangle of a 1/4-resolution mesh built around the
+// depth-discontinuity pixels.  Here every mesh patch rasterises its own two triangles: the Moeller-Trumbore test is
+// only evaluated for the pixels inside the triangle's (conservative) screen bounding box and the nearest hit is an
+// atomicMin on the float bits (t > 0, so the unsigned order is the float order) — the same set of (ray, triangle)
+// hits, order independent and therefore deterministic.
+// ------------------------------------------------------------------------------------------------
+struct AxisTap {
+  int i0, i1;
+  float lam;
+};
+// F.interpolate(mode="bilinear", align_corners=False) along one axis
+__device__ __forceinline__ AxisTap bilinear_tap(int dst, int n_in, int n_out) {
+  const float scale = (float)n_in / (float)n_out;
+  float src = fmaxf(((float)dst + 0.5f) * scale - 0.5f, 0.0f);
+  AxisTap t;
+  t.i0 = min((int)floorf(src), n_in - 1);
+  t.i1 = min(t.i0 + 1, n_in - 1);
+  t.lam = src - (float)t.i0;
+  return t;
+}
+
+// vertices of the 1/4-resolution mesh: bilinear resample of the camera-space points (w2c . [p;1]) of one item, plus
+// the nearest-resampled boundary mask.  verts [item][nh][nw][3], vmask [item][nh][nw]
+__global__ void __launch_bounds__(256)
+    k_fg_mesh_points(const float* __restrict__ points, const uint8_t* __restrict__ boundary,
+                     const float* __restrict__ w2c, int H, int W, int nh, int nw, float* __restrict__ verts,
+                     uint8_t* __restrict__ vmask) {
+  const int item = blockIdx.y;
+  const float* m = w2c + 16 * item;
+  const float* p = points + (size_t)item * H * W * 3;
+  const uint8_t* bm = boundary + (size_t)item * H * W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nh * nw; i += gridDim.x * blockDim.x) {
+    const int vy = i / nw, vx = i - vy * nw;
+    const AxisTap ty = bilinear_tap(vy, H, nh), tx = bilinear_tap(vx, W, nw);
+    float acc[3] = {0.f, 0.f, 0.f};
+    const int ys[2] = {ty.i0, ty.i1}, xs[2] = {tx.i0, tx.i1};
+    const float wy[2] = {1.0f - ty.lam, ty.lam}, wx[2] = {1.0f - tx.lam, tx.lam};
+    float row[2][3];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      float c[2][3];
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const float* q = p + ((size_t)ys[a] * W + xs[b]) * 3;
+        const float px = q[0], py = q[1], pz = q[2];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+          c[b][r] = __fadd_rn(__fmaf_rn(m[4 * r + 2], pz, __fmaf_rn(m[4 * r + 1], py, __fmul_rn(m[4 * r], px))), m[4 * r + 3]);
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) row[a][r] = c[0][r] * wx[0] + c[1][r] * wx[1];
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) acc[r] = row[0][r] * wy[0] + row[1][r] * wy[1];
+    float* o = verts + ((size_t)item * nh * nw + i) * 3;
+    o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2];
+    // mode="nearest": source index floor(dst * in / out)
+    const int sy = min((int)floorf((float)vy * ((float)H / (float)nh)), H - 1);
+    const int sx = min((int)floorf((float)vx * ((float)W / (float)nw)), W - 1);
+    vmask[(size_t)item * nh * nw + i] = bm[(size_t)sy * W + sx] ? 1 : 0;
+  }
+}
+
+struct Ray {
+  float x, y, z;
+};
+// get_camera_rays :151-168: normalised K^-1 (x, y, 1)
+__device__ __forceinline__ Ray camera_ray(const float* __restrict__ kinv, int x, int y) {
+  const float fx = (float)x, fy = (float)y;
+  float ux = __fadd_rn(__fmaf_rn(kinv[1], fy, __fmul_rn(kinv[0], fx)), kinv[2]);
+  float uy = __fadd_rn(__fmaf_rn(kinv[4], fy, __fmul_rn(kinv[3], fx)), kinv[5]);
+  float uz = __fadd_rn(__fmaf_rn(kinv[7], fy, __fmul_rn(kinv[6], fx)), kinv[8]);
+  float n = sqrtf(ux * ux + uy * uy + uz * uz);
+  if (n == 0.0f) n = 1.0f;
+  Ray r;
+  r.x = ux / n; r.y = uy / n; r.z = uz / n;
+  return r;
+}
+
+// Moeller-Trumbore for a ray from the origin (the target camera centre); returns t or 0 (ray_triangle_intersection_warp.py:56-105)
+__device__ __forceinline__ float ray_tri(const Ray& d, const float* v0, const float* v1, const float* v2, float eps) {
+  const float e1x = v1[0] - v0[0], e1y = v1[1] - v0[1], e1z = v1[2] - v0[2];
+  const float e2x = v2[0] - v0[0], e2y = v2[1] - v0[1], e2z = v2[2] - v0[2];
+  const float hx = d.y * e2z - d.z * e2y, hy = d.z * e2x - d.x * e2z, hz = d.x * e2y - d.y * e2x;
+  const float a = e1x * hx + e1y * hy + e1z * hz;
+  if (fabsf(a) < eps) return 0.0f;
+  const float f = 1.0f / a;
+  const float sx = -v0[0], sy = -v0[1], sz = -v0[2];
+  const float u = f * (sx * hx + sy * hy + sz * hz);
+  if (u < 0.0f || u > 1.0f) return 0.0f;
+  const float qx = sy * e1z - sz * e1y, qy = sz * e1x - sx * e1z, qz = sx * e1y - sy * e1x;
+  const float v = f * (d.x * qx + d.y * qy + d.z * qz);
+  if (v < 0.0f || (u + v) > 1.0f) return 0.0f;
+  const float t = f * (e2x * qx + e2y * qy + e2z * qz);
+  return t > eps ? t : 0.0f;
+}
+
+// one thread per mesh patch (u, v): its two triangles (tl, tr, bl) and (tr, br, bl) when any corner is on the boundary
+__global__ void __launch_bounds__(256)
+    k_fg_raster(const float* __restrict__ verts, const uint8_t* __restrict__ vmask, const float* __restrict__ K,
+                const float* __restrict__ Kinv, int H, int W, int nh, int nw, uint32_t* __restrict__ tbuf) {
+  const int item = blockIdx.y;
+  const float* k = K + 9 * item;
+  const float* kinv = Kinv + 9 * item;
+  const float* vb = verts + (size_t)item * nh * nw * 3;
+  const uint8_t* mb = vmask + (size_t)item * nh * nw;
+  uint32_t* tb = tbuf + (size_t)item * H * W;
+  const int np = (nh - 1) * (nw - 1);
+  for (int pidx = blockIdx.x * blockDim.x + threadIdx.x; pidx < np; pidx += gridDim.x * blockDim.x) {
+    const int u = pidx / (nw - 1), v = pidx - u * (nw - 1);
+    const int itl = u * nw + v, itr = itl + 1, ibl = itl + nw, ibr = ibl + 1;
+    if (!(mb[itl] | mb[itr] | mb[ibl] | mb[ibr])) continue;
+    const int tri[2][3] = {{itl, itr, ibl}, {itr, ibr, ibl}};
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t) {
+      const float* v0 = vb + 3 * tri[t][0];
+      const float* v1 = vb + 3 * tri[t][1];
+      const float* v2 = vb + 3 * tri[t][2];
+      // conservative screen bounding box; a vertex at or behind the camera plane makes the whole frame the box
+      int x0 = 0, x1 = W - 1, y0 = 0, y1 = H - 1;
+      const float zmin = fminf(v0[2], fminf(v1[2], v2[2]));
+      if (zmin > 1e-4f) {
+        float xmin = 3.0e38f, xmax = -3.0e38f, ymin = 3.0e38f, ymax = -3.0e38f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float* vv = c == 0 ? v0 : (c == 1 ? v1 : v2);
+          const float px = (k[0] * vv[0] + k[1] * vv[1] + k[2] * vv[2]) / (k[6] * vv[0] + k[7] * vv[1] + k[8] * vv[2]);
+          const float py = (k[3] * vv[0] + k[4] * vv[1] + k[5] * vv[2]) / (k[6] * vv[0] + k[7] * vv[1] + k[8] * vv[2]);
+          xmin = fminf(xmin, px); xmax = fmaxf(xmax, px);
+          ymin = fminf(ymin, py); ymax = fmaxf(ymax, py);
+        }
+        if (!(xmax >= -2.0f && ymax >= -2.0f && xmin <= (float)W + 1.0f && ymin <= (float)H + 1.0f)) continue;  // off screen (or NaN)
+        x0 = max(0, (int)floorf(xmin) - 1); x1 = min(W - 1, (int)ceilf(xmax) + 1);
+        y0 = max(0, (int)floorf(ymin) - 1); y1 = min(H - 1, (int)ceilf(ymax) + 1);
+      }
+      for (int y = y0; y <= y1; ++y)
+        for (int x = x0; x <= x1; ++x) {
+          const Ray d = camera_ray(kinv, x, y);
+          const float tt = ray_tri(d, v0, v1, v2, 1e-8f);
+          if (tt > 0.0f) atomicMin(tb + (size_t)y * W + x, __float_as_uint(tt));
+        }
+    }
+  }
+}
+
+// :317-334: mesh z-depth = t * ray_z (the bilinear resample to the same size is the identity), pixels whose mesh depth
+// is more than 0.02 in front of the splatted depth are removed from mask / image (fill -1) / depth
+__global__ void __launch_bounds__(256)
+    k_fg_apply(const uint32_t* __restrict__ tbuf, const float* __restrict__ Kinv, int C, int H, int W,
+               float* __restrict__ warped, float* __restrict__ mask, float* __restrict__ depth) {
+  const int item = blockIdx.y;
+  const int HW = H * W;
+  const float* kinv = Kinv + 9 * item;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+    const uint32_t bits = tbuf[(size_t)item * HW + i];
+    if (bits >= 0x7F800000u) continue;  // no hit (initialised to 0xFFFFFFFF)
+    const int y = i / W, x = i - y * W;
+    const float mesh_z = __uint_as_float(bits) * camera_ray(kinv, x, y).z;
+    float* dz = depth + (size_t)item * HW + i;
+    if (mesh_z > 0.0f && (mesh_z + 0.02f) < *dz) {
+      *dz = 0.0f;
+      mask[(size_t)item * HW + i] = 0.0f;
+      // (warped + 1) * 0 - 1 (:333): -1 whatever the frame holds
+      for (int c = 0; c < C; ++c) warped[((size_t)item * C + c) * HW + i] = -1.0f;
+    }
+  }
+}
+
+__global__ void k_fg_invert_k(const float* __restrict__ K, int n, float* __restrict__ Kinv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) invert_small(K + 9 * i, 3, Kinv + 9 * i);
+}
+
 static inline dim3 px_grid(int HW, int items) {
   int bx = (HW + 255) / 256;
   int cap = 4 * sm_count();
@@ -539,6 +716,33 @@ int g3c_reliable_depth_mask(const float* depth, int b, int H, int W, int window,
   k_reliable_mask<<<px_grid(H * W, b), 256, 0, (cudaStream_t)stream>>>(depth, H, W, window,
                                                                        ratio_thresh, eps, out);
   G3C_CUDA(cudaGetLastError());
+  return G3C_OK;
+}
+
+int g3c_foreground_occlusion(const float* points, const uint8_t* boundary, const float* w2c, const float* K, int b, int C,
+                             int H, int W, float* warped, float* mask, float* depth, void* stream) {
+  G3C_REQUIRE(points && boundary && w2c && K && warped && mask && depth, "foreground_occlusion: null argument");
+  G3C_REQUIRE(b > 0 && b <= 65535 && C >= 1 && C <= 3 && H >= 8 && W >= 8, "foreground_occlusion: bad sizes");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nh = H / 4, nw = W / 4;  // mesh_downsample_factor = 4 (:289)
+  const size_t nv = (size_t)b * nh * nw;
+  float *verts = nullptr, *kinv = nullptr;
+  uint8_t* vmask = nullptr;
+  uint32_t* tbuf = nullptr;
+  G3C_CUDA(cudaMallocAsync(&verts, nv * 3 * sizeof(float), st));
+  G3C_CUDA(cudaMallocAsync(&vmask, nv, st));
+  G3C_CUDA(cudaMallocAsync(&kinv, (size_t)b * 9 * sizeof(float), st));
+  G3C_CUDA(cudaMallocAsync(&tbuf, (size_t)b * H * W * sizeof(uint32_t), st));
+  G3C_CUDA(cudaMemsetAsync(tbuf, 0xFF, (size_t)b * H * W * sizeof(uint32_t), st));
+  k_fg_invert_k<<<(b + 63) / 64, 64, 0, st>>>(K, b, kinv);
+  k_fg_mesh_points<<<px_grid(nh * nw, b), 256, 0, st>>>(points, boundary, w2c, H, W, nh, nw, verts, vmask);
+  k_fg_raster<<<px_grid((nh - 1) * (nw - 1), b), 256, 0, st>>>(verts, vmask, K, kinv, H, W, nh, nw, tbuf);
+  k_fg_apply<<<px_grid(H * W, b), 256, 0, st>>>(tbuf, kinv, C, H, W, warped, mask, depth);
+  G3C_CUDA(cudaGetLastError());
+  G3C_CUDA(cudaFreeAsync(verts, st));
+  G3C_CUDA(cudaFreeAsync(vmask, st));
+  G3C_CUDA(cudaFreeAsync(kinv, st));
+  G3C_CUDA(cudaFreeAsync(tbuf, st));
   return G3C_OK;
 }
 

@@ -6,6 +6,7 @@ function).  Tensors are CUDA float32; there is no CPU path.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -133,7 +134,12 @@ def forward_warp(
     if conditioned_normal1 is not None or cameraray_filtering:
         raise NotImplementedError("normal / camera-ray filtering is not on the GEN3C inference path")
     if foreground_masking:
-        raise NotImplementedError("foreground_masking (mesh occlusion pass) is SURVEY.md §8(f) rank 1: not built yet")
+        # SURVEY.md §8(f) rank 1.  The native pass (g3c_foreground_occlusion) exists together with its CPU restatement and golden vector,
+        # but has not run on hardware yet: it stays opt-in until its GPU parity test has passed on a B200.
+        if os.environ.get("G3C_EXPERIMENTAL_FOREGROUND", "0") != "1":
+            raise NotImplementedError("foreground_masking (mesh occlusion pass, SURVEY.md §8(f) rank 1) is experimental: "
+                                      "set G3C_EXPERIMENTAL_FOREGROUND=1 to use the unvalidated native pass")
+        assert boundary_mask is not None
     b, c, h, w = frame1.shape
     if intrinsic2 is None:
         assert intrinsic1 is not None, "intrinsic2 cannot be derived if intrinsic1 is None and intrinsic2 is None"
@@ -157,8 +163,9 @@ def forward_warp(
     warped = torch.empty_like(frame1)
     mask2 = torch.empty((b, 1, h, w), device=dev, dtype=torch.float32)
     flow = torch.empty((b, 2, h, w), device=dev, dtype=torch.float32)
-    depth2 = torch.empty((b, h, w), device=dev, dtype=torch.float32) if render_depth else None
-    flags = (1 if render_depth else 0) | (0 if is_image else 2)
+    want_depth = render_depth or foreground_masking
+    depth2 = torch.empty((b, h, w), device=dev, dtype=torch.float32) if want_depth else None
+    flags = (1 if want_depth else 0) | (0 if is_image else 2)
     lib = _lib.load()
     with torch.cuda.device(dev):
         ws = _workspace(h, w, dev)
@@ -167,6 +174,14 @@ def forward_warp(
                                         _lib.ptr(_f32c(intrinsic2, "intrinsic2")), b, c, flags, _lib.ptr(warped),
                                         _lib.ptr(mask2), _lib.ptr(depth2), _lib.ptr(flow), _lib.stream_ptr()),
                    "g3c_forward_warp")
+        if foreground_masking:
+            assert boundary_mask.shape == (b, h, w)
+            bm = boundary_mask.to(device=dev, dtype=torch.uint8).contiguous()
+            _lib.check(lib.g3c_foreground_occlusion(_lib.ptr(points), _lib.ptr(bm),
+                                                    _lib.ptr(_f32c(transformation2, "transformation2")),
+                                                    _lib.ptr(_f32c(intrinsic2, "intrinsic2")), b, c, h, w, _lib.ptr(warped),
+                                                    _lib.ptr(mask2), _lib.ptr(depth2), _lib.stream_ptr()),
+                       "g3c_foreground_occlusion")
     return warped, mask2, depth2, flow
 
 

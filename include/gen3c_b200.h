@@ -83,6 +83,16 @@ int g3c_unproject_points(const float* depth, const float* w2c, const float* K, c
 int g3c_reliable_depth_mask(const float* depth, int b, int H, int W, int window, float ratio_thresh,
                             float eps, uint8_t* out, void* stream);
 
+/* EXPERIMENTAL (not yet validated on hardware): the foreground-masking occlusion pass of
+ * forward_warp(foreground_masking=True, boundary_mask=...) — reference forward_warp_utils_pytorch.py:285-335 with
+ * points_to_mesh :49-132, get_camera_rays :151-168 and the NVIDIA-Warp kernel ray_triangle_intersection_warp.py:23-105.
+ * Post-processes the outputs of g3c_forward_warp(..., G3C_WARP_RENDER_DEPTH): pixels whose 1/4-resolution boundary mesh
+ * lies more than 0.02 in front of the splatted depth are cleared (mask 0, image -1, depth 0).
+ *   points [b,H,W,3] f32 world points, boundary [b,H,W] u8, w2c [b,4,4], K [b,3,3]; in/out warped [b,C,H,W],
+ *   mask [b,1,H,W], depth [b,H,W]. */
+int g3c_foreground_occlusion(const float* points, const unsigned char* boundary, const float* w2c, const float* K, int b,
+                             int C, int H, int W, float* warped, float* mask, float* depth, void* stream);
+
 /* ===================================== Path D: DiT denoise step =============================== */
 
 #define G3C_EPI_BF16 0               /* D (bf16) = acc                          */

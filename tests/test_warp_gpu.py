@@ -125,6 +125,30 @@ def test_full_size_identity_roundtrip():
     assert float((pix[0, :, 0] - pair).abs().max()) <= 1e-5
 
 
+@pytest.mark.skipif(os.environ.get("G3C_EXPERIMENTAL_FOREGROUND", "0") != "1",
+                    reason="foreground-masking pass (SURVEY.md 8f rank 1) is opt-in until validated on hardware")
+def test_foreground_masking_matches_reference_golden(golden_dir):
+    """forward_warp(foreground_masking=True): the native occlusion pass against the golden minted from the reference's
+    own forward_warp (tests/golden/warp_R7_foreground.npz).  Occlusion decisions may flip only on knife-edge pixels
+    (mesh depth within float round-off of `splatted depth - 0.02`)."""
+    from gen3c_b200 import warp
+
+    g = np.load(os.path.join(golden_dir, "warp_R7_foreground.npz"))
+    c = cases.foreground_case()
+    w, m, d, _ = warp.forward_warp(cu(c["image"]), None, None, None, cu(c["w2c_tgt"]), cu(c["K"]), cu(c["K"]),
+                                   world_points1=cu(g["points"]), foreground_masking=True, boundary_mask=cu(g["boundary"]))
+    torch.cuda.synchronize()
+    w, m, d = (t.cpu().numpy() for t in (w, m, d))
+    occluded_ref = (g["mask_plain"] > 0) & (g["mask"] == 0)
+    occluded = (g["mask_plain"] > 0) & (m == 0)
+    assert occluded_ref.mean() > 0.02
+    assert (occluded != occluded_ref).mean() < 2e-3
+    same = (m == g["mask"])
+    sel = np.broadcast_to(same, w.shape)
+    assert close_frac(w[sel], g["warped"][sel], 2e-3) > 0.999
+    assert close_frac(d[same[:, 0]], g["depth"][same[:, 0]], 1e-3) > 0.999
+
+
 def test_error_behaviour():
     from gen3c_b200 import warp
 
