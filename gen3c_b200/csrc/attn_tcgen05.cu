@@ -23,11 +23,10 @@
 // the whole PV/S pair of the other overlap with that tile's softmax.  P is released to the MMA warp
 // in two 64-key halves, so the first four P·V k-steps run under the second half of the exponentials.
 // Per tile the dependent chain is  S MMA -> softmax -> PV MMA -> (P columns free) -> next S MMA, so
-// the softmax LATENCY of one tile, not its throughput, sets the step period (clock64 timelines:
-// profiles/r01_attn_v1_timeline.txt).  Hence (kMode 1): the row max is reduced in the shadow of the
-// exponentials of the first half, which speculatively use the previous reference max; O / row sum are
-// only rescaled (and that half recomputed) when the max grew past the lazy threshold — rare after
-// the first KV tiles; fp32x2 packed FFMA/FADD and 3-input max halve the non-MUFU issue slots.
+// the softmax latency of one tile sets the step period (clock64 timelines: profiles/r01_attn_v1_timeline.txt),
+// and the GPU is power-capped under this kernel: what pays is fewer instructions per score.  Hence the
+// default softmax (kMode 2, see below): no per-tile row max, no scale-subtract when Q carries the scale,
+// FADD2 row sums.  CTA pairs share every K / V tile through TMA multicast (kCluster).
 #include <cmath>
 #include <cstdlib>
 
