@@ -56,6 +56,8 @@ class StepArgs(C.Structure):
         ("sigma_aug", C.c_float),
         ("guidance", C.c_float),
         ("xt_next", C.c_void_p),
+        ("cond_mask_uncond", C.c_void_p),
+        ("net_output", C.c_void_p),
     ]
 
 
@@ -76,7 +78,9 @@ SIGNATURES = {
     "g3c_splat_indices": (_I, [_P, _I, _I, _I, _P, _P]),
     "g3c_unproject_points": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "g3c_reliable_depth_mask": (_I, [_P, _I, _I, _I, _I, _F, _F, _P, _P]),
+    "g3c_align_depth_nonrigid": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _F, _F, _P, _P]),
     "g3c_foreground_occlusion": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "g3c_render_cache_occlusion": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P]),
     "g3c_gemm_bf16": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P]),
     "g3c_gemm_norm_rope_bf16": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _F, _P]),
     "g3c_attn_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P]),
@@ -92,11 +96,15 @@ SIGNATURES = {
     "g3c_dit_cp_import": (_I, [_P, _P, _I]),
     "g3c_dit_cp_mode": (_I, [_P]),
     "g3c_dit_disable_cp": (_I, [_P]),
+    "g3c_dit_enable_cfg_parallel": (_I, [_P, _I]),
+    "g3c_dit_cfg_export": (_I, [_P, _P]),
+    "g3c_dit_cfg_import": (_I, [_P, _P]),
     "g3c_dit_set_shape": (_I, [_P, _I, _I, _I, _I, _F]),
     "g3c_dit_forward": (_I, [_P, _P, _P, _P, _P, _F, _P, _P, _P]),
     "g3c_denoise_step": (_I, [_P, C.POINTER(StepArgs), _P]),
     "g3c_dit_profile": (_I, [_P, _I]),
     "g3c_dit_profile_read": (_I, [_P, C.POINTER(_F), C.POINTER(_I), _I]),
+    "g3c_dit_profile_wait_ms": (_I, [_P, C.POINTER(_F)]),
     "g3c_dit_workspace_bytes": (C.c_int64, [_P]),
     "g3c_dit_last_launch_count": (_I, [_P]),
 }

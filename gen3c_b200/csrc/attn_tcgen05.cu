@@ -51,6 +51,9 @@ struct AttnParams {
   const uint32_t* chunk_flags;  // context-parallel gate (or NULL): chunk c readable once chunk_flags[c] >= flag_seq
   uint32_t flag_seq;
   int first_chunk;
+  unsigned long long peer_timeout_ns;  // bound of the wait for a peer's chunk flag (and of this CTA's barrier waits
+                                       // while such a wait may be pending): an inter-process dependency, not a protocol bug
+  unsigned long long* wait_ns;         // optional profiling counter: ns spent polling chunk flags, summed over CTAs
   int unit_scale;             // 1: scale_log2 == 1 (the caller folded softmax scale * log2 e into Q): S is in log2 units
   int p_halves;               // 1: P is released to the MMA warp per 64-key half, 0: per 128-key tile
   unsigned long long* trace;  // kTrace only: [3 roles][64 steps][8 slots] clock64 stamps of CTA (0,0)
@@ -187,17 +190,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           for (;;) {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p.chunk_flags + chunk) : "memory");
             if ((int)(v - p.flag_seq) >= 0) break;
-            if ((++spins & 0x3FFu) == 0) {
-              const uint64_t now = global_timer_ns();
-              if (t0 == 0) t0 = now;
-              else if (now - t0 > G3C_MBAR_TIMEOUT_NS) asm volatile("trap;\n");
-            }
+            if (t0 == 0) t0 = global_timer_ns();
+            if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > p.peer_timeout_ns) asm volatile("trap;\n");
           }
+          if (t0 != 0 && p.wait_ns) atomicAdd(p.wait_ns, (unsigned long long)(global_timer_ns() - t0));
           asm volatile("fence.proxy.async.global;\n" ::: "memory");  // peer-written data is read by the TMA next
         }
         const int kv0 = chunk * p.vt_chunk_len + within * ATT_TILE;
         // K_j
-        mbar_wait(&kv_empty[slot], phase ^ 1);
+        mbar_wait_ns(&kv_empty[slot], phase ^ 1, p.peer_timeout_ns);
         mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
         if constexpr (kCluster) {
           tma_load_2d_mc(smem_kv + slot * ATT_TILE_BYTES + crank * ATT_HALF_BYTES, &tmK, &kv_full[slot],
@@ -210,7 +211,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         }
         if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; }
         // V_j  (transposed: rows = head dim, columns = keys)
-        mbar_wait(&kv_empty[slot], phase ^ 1);
+        mbar_wait_ns(&kv_empty[slot], phase ^ 1, p.peer_timeout_ns);
         mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
         const int koff = within * ATT_TILE;
         if constexpr (kCluster) {
@@ -256,8 +257,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           umma_ts(tO[t], tS[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
         }
       };
-      if (pass == 0) mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[slot], phase);
+      if (pass == 0) mbar_wait_ns(q_full, 0, p.peer_timeout_ns);
+      mbar_wait_ns(&kv_full[slot], phase, p.peer_timeout_ns);
       tc_fence_after();
       uint32_t kslot = slot;
       advance();
@@ -268,21 +269,21 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       release_slot(kslot);
       for (int j = 0; j < n_kv; ++j) {
         const bool more = j + 1 < n_kv;
-        mbar_wait(&kv_full[slot], phase);  // V_j
+        mbar_wait_ns(&kv_full[slot], phase, p.peer_timeout_ns);  // V_j
         const uint32_t vslot = slot;
         advance();
         // ---- tile A
         ATT_TR(0, 0);
         // the P·V MMAs of the first 64 keys start while the softmax still exponentiates the second 64
-        mbar_wait(&p_half[0], pph);
+        mbar_wait_ns(&p_half[0], pph, p.peer_timeout_ns);
         ATT_TR(0, 1);
         tc_fence_after();
         mma_pv(0, vslot, j == 0, 0);
-        mbar_wait(&p_half[1], pph);
+        mbar_wait_ns(&p_half[1], pph, p.peer_timeout_ns);
         tc_fence_after();
         mma_pv(0, vslot, j == 0, 1);
         if (more) {
-          mbar_wait(&kv_full[slot], phase);  // K_{j+1}
+          mbar_wait_ns(&kv_full[slot], phase, p.peer_timeout_ns);  // K_{j+1}
           tc_fence_after();
           kslot = slot;
           advance();
@@ -291,11 +292,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         umma_commit(&s_full[0]);
         ATT_TR(0, 2);
         // ---- tile B
-        mbar_wait(&p_half[2], pph);
+        mbar_wait_ns(&p_half[2], pph, p.peer_timeout_ns);
         ATT_TR(0, 3);
         tc_fence_after();
         mma_pv(1, vslot, j == 0, 0);
-        mbar_wait(&p_half[3], pph);
+        mbar_wait_ns(&p_half[3], pph, p.peer_timeout_ns);
         tc_fence_after();
         mma_pv(1, vslot, j == 0, 1);
         release_slot(vslot);
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     };
     auto wait_s = [&](int j) {
       if (tr) ATT_TR(1 + t, 0);
-      mbar_wait(&s_full[t], sphase);
+      mbar_wait_ns(&s_full[t], sphase, p.peer_timeout_ns);
       if (tr) ATT_TR(1 + t, 1);
       sphase ^= 1;
       tc_fence_after();
@@ -486,7 +487,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       for (int j = 1; j < n_kv; ++j) tile_fast(j);
     }
     // final: PV(n_kv-1) complete
-    mbar_wait(&s_full[t], sphase);
+    mbar_wait_ns(&s_full[t], sphase, p.peer_timeout_ns);
     sphase ^= 1;
     tc_fence_after();
     if constexpr (kMode == 2) {
@@ -605,6 +606,8 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
   if (p.unit_scale) p.scale_log2 = 1.0f;
   dim3 grid((Lq + 2 * ATT_TILE - 1) / (2 * ATT_TILE), heads);
   p.chunk_flags = gate ? gate->flags : nullptr;
+  p.peer_timeout_ns = gate ? peer_timeout_ns() : G3C_MBAR_TIMEOUT_NS;
+  p.wait_ns = gate ? gate->wait_ns : nullptr;
   p.flag_seq = gate ? gate->seq : 0;
   p.first_chunk = gate ? gate->first : 0;
   static int halves = -1;

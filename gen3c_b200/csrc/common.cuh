@@ -141,6 +141,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, with a run-time bound: kernels whose progress depends on another PROCESS (context-parallel K/V arrival) pass
+// the inter-process timeout so that rank skew of seconds (lazy module load, allocation, host jitter) is waited out.
+__device__ __forceinline__ void mbar_wait_ns(uint64_t* bar, uint32_t parity, unsigned long long timeout_ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xFFFu) == 0) {
+      uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > timeout_ns) G3C_MBAR_TIMEOUT_ACTION(smem_u32(bar), parity);
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMA loads (tile mode, mbarrier completion)
 // ----------------------------------------------------------------------------------------------

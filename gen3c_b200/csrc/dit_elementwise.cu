@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(256)
                    const __nv_bfloat16* __restrict__ ou, const __nv_bfloat16* __restrict__ gt,
                    const float* __restrict__ ind_t, int T, size_t plane, size_t n, float guidance,
                    float sigma, float sigma_next, float sigma_aug, float sd,
-                   __nv_bfloat16* __restrict__ xnext) {
+                   __nv_bfloat16* __restrict__ xnext, __nv_bfloat16* __restrict__ net_out) {
   const float c_skip = sd * sd / (sigma * sigma + sd * sd);
   const float c_out = sigma * sd / sqrtf(sigma * sigma + sd * sd);
   const bool aug_on = !(sigma_aug >= sigma);
@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(256)
     float ind = aug_on ? ind_t[t] : 0.0f;
     float c = __bfloat162float(oc[i]), u = __bfloat162float(ou[i]);
     float o = c + guidance * (c - u);
+    if (net_out) net_out[i] = __float2bfloat16_rn(o);  // net_output of model_v2w.py:143 (test / inspection hook)
     float xs = __bfloat162float(xtilde[i]);
     float lat = (__bfloat162float(gt[i]) - c_skip * xs) / c_out;
     o = ind * lat + (1.0f - ind) * o;
@@ -421,10 +422,10 @@ int sampler_pre(const __nv_bfloat16* xt, const __nv_bfloat16* gt, const float* n
 int sampler_post(const __nv_bfloat16* xtilde, const __nv_bfloat16* oc, const __nv_bfloat16* ou,
                  const __nv_bfloat16* gt, const float* ind_t, int C, int T, size_t plane, float guidance,
                  float sigma, float sigma_next, float sigma_aug, float sd, __nv_bfloat16* xnext,
-                 cudaStream_t st) {
+                 __nv_bfloat16* net_out, cudaStream_t st) {
   size_t n = (size_t)C * T * plane;
   k_sampler_post<<<4 * sm_count(), 256, 0, st>>>(xtilde, oc, ou, gt, ind_t, T, plane, n, guidance, sigma,
-                                                 sigma_next, sigma_aug, sd, xnext);
+                                                 sigma_next, sigma_aug, sd, xnext, net_out);
   G3C_CUDA(cudaGetLastError());
   return G3C_OK;
 }

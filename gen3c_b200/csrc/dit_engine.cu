@@ -135,6 +135,19 @@ struct g3c_dit {
         *vec_emb = nullptr, *vec_h1 = nullptr, *vec_lora = nullptr, *vec_a = nullptr, *freqs = nullptr;
   __nv_bfloat16 *lat_xtilde = nullptr, *lat_xin = nullptr, *lat_oc = nullptr, *lat_ou = nullptr;
   bool tables_ready = false;
+  // the B=1 modulation vectors depend on the timestep only: the second forward of a denoise step reuses them
+  bool mods_valid = false;
+  float mods_timestep = 0.f;
+  // classifier-free-guidance parallelism: this rank evaluates one branch (0 cond / 1 uncond); the partner holds the
+  // other.  Exchange region (IPC-mapped by the partner): 2 slots of one latent + 2 arrival flags.
+  int cfg_role = -1;
+  void* cfg_region = nullptr;
+  void* cfg_peer = nullptr;
+  size_t cfg_slot_bytes = 0;
+  uint32_t cfg_seq = 0;
+  // attention kernel: ns spent polling peer flags (summed over CTAs), CTA count of those launches
+  unsigned long long* wait_ns = nullptr;
+  double wait_cta_launches = 0.0;
   int launches = 0;
   // optional per-category device timing (bench.py roofline): events around every launch
   bool prof = false;
@@ -272,6 +285,38 @@ __global__ void k_cp_signal(PeerDst slots, uint32_t seq) {
   }
 }
 
+// Stream-ordered wait for a peer's flag (CFG-parallel output exchange): one warp polls with system-scope acquire loads.
+// The data the flag covers was written by the peer's copy engine into this GPU's memory, no SM of this GPU is needed for
+// it to arrive, so a resident spinning warp cannot block its own producer.
+__global__ void k_wait_flag(const uint32_t* flag, uint32_t seq, unsigned long long timeout_ns) {
+  if (threadIdx.x != 0) return;
+  uint32_t v, spins = 0;
+  uint64_t t0 = 0;
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(flag) : "memory");
+    if ((int)(v - seq) >= 0) break;
+    __nanosleep(200);
+    if ((++spins & 0xFFu) == 0) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > timeout_ns) asm volatile("trap;\n");
+    }
+  }
+}
+
+// Inter-process waits (peer K/V flags, CFG partner) may legitimately take as long as the slowest rank's first-step
+// set-up: their bound is separate from the 4 s intra-CTA protocol timeout and configurable (G3C_PEER_TIMEOUT_S, 600 s).
+unsigned long long peer_timeout_ns() {
+  static unsigned long long v = 0;
+  if (!v) {
+    const char* e = getenv("G3C_PEER_TIMEOUT_S");
+    double sec = e ? atof(e) : 600.0;
+    if (!(sec > 0)) sec = 600.0;
+    v = (unsigned long long)(sec * 1e9);
+  }
+  return v;
+}
+
 static int build_tables(g3c_dit* h, cudaStream_t st) {
   if (h->tables_ready) return G3C_OK;
   const g3c_dit_config& c = h->cfg;
@@ -299,6 +344,7 @@ static int build_tables(g3c_dit* h, cudaStream_t st) {
 static int forward(g3c_dit* h, const void* x_in, const void* cond_mask, const void* cond_pose,
                    const void* padding_mask, float timestep, const void* ctx, void* out,
                    cudaStream_t st) {
+  static_assert(sizeof(float) == 4, "");
   G3C_REQUIRE(h && x_in && cond_mask && ctx && out, "dit_forward: null argument");
   G3C_REQUIRE(h->L > 0, "dit_forward: g3c_dit_set_shape was not called");
   TRY(resolve(h, st));
@@ -351,17 +397,22 @@ static int forward(g3c_dit* h, const void* x_in, const void* cond_mask, const vo
 
   // ---- timestep embedding + all adaLN-LoRA modulation vectors (blocks.py:38-80, :442-445;
   //      general_dit.py:405).  They depend on t only.
-  K(CAT_VECTOR, timestep_embed(timestep, D, h->affine_gamma, 1e-6f, h->vec_s, h->vec_emb, st));
-  K(CAT_VECTOR, gemv(h->w_t1, h->vec_s, nullptr, h->vec_h1, D, D, 0, 0, st));
-  K(CAT_VECTOR, gemv(h->w_t2, h->vec_h1, nullptr, h->vec_lora, 3 * D, D, 1, 0, st));
-  for (int i = 0; i < c.num_blocks; ++i)
-    for (int j = 0; j < 3; ++j) {
-      const SubBlock& s = h->blk[i][j];
-      K(CAT_VECTOR, gemv(s.ada1, h->vec_emb, nullptr, h->vec_a, R, D, 1, 0, st));
-      K(CAT_VECTOR, gemv(s.ada2, h->vec_a, h->vec_lora, h->mods + (size_t)(i * 3 + j) * 3 * D, 3 * D, R, 0, 0, st));
-    }
-  K(CAT_VECTOR, gemv(h->f_ada1, h->vec_emb, nullptr, h->vec_a, R, D, 1, 0, st));
-  K(CAT_VECTOR, gemv(h->f_ada2, h->vec_a, h->vec_lora, h->modf, 2 * D, R, 0, 0, st));
+  //      cond and uncond forward of one denoise step share t (model_v2w.py:140-142): computed once per timestep.
+  if (!(h->mods_valid && h->mods_timestep == timestep)) {
+    K(CAT_VECTOR, timestep_embed(timestep, D, h->affine_gamma, 1e-6f, h->vec_s, h->vec_emb, st));
+    K(CAT_VECTOR, gemv(h->w_t1, h->vec_s, nullptr, h->vec_h1, D, D, 0, 0, st));
+    K(CAT_VECTOR, gemv(h->w_t2, h->vec_h1, nullptr, h->vec_lora, 3 * D, D, 1, 0, st));
+    for (int i = 0; i < c.num_blocks; ++i)
+      for (int j = 0; j < 3; ++j) {
+        const SubBlock& s = h->blk[i][j];
+        K(CAT_VECTOR, gemv(s.ada1, h->vec_emb, nullptr, h->vec_a, R, D, 1, 0, st));
+        K(CAT_VECTOR, gemv(s.ada2, h->vec_a, h->vec_lora, h->mods + (size_t)(i * 3 + j) * 3 * D, 3 * D, R, 0, 0, st));
+      }
+    K(CAT_VECTOR, gemv(h->f_ada1, h->vec_emb, nullptr, h->vec_a, R, D, 1, 0, st));
+    K(CAT_VECTOR, gemv(h->f_ada2, h->vec_a, h->vec_lora, h->modf, 2 * D, R, 0, 0, st));
+    h->mods_valid = true;
+    h->mods_timestep = timestep;
+  }
 
   __nv_bfloat16* k_loc = h->k_all + (size_t)h->cp_rank * L * D;
   __nv_bfloat16* vt_loc = h->vt_all + (size_t)h->cp_rank * L * D;
@@ -429,6 +480,8 @@ static int forward(g3c_dit* h, const void* x_in, const void* cond_mask, const vo
         gate.flags = (const uint32_t*)(reg + h->off_flags) + set * 8;
         gate.seq = seq;
         gate.first = me;
+        gate.wait_ns = h->prof ? h->wait_ns : nullptr;
+        h->wait_cta_launches = (double)((L + 255) / 256) * heads;  // CTAs of one gated launch
         K(CAT_ATTN_SELF, attn_fwd(h->q, kb, vb, h->att, L, Lk_all, heads, D, D, D, L, attn_scale, st, &gate));
       } else {
         TRY(proj_norm_rope(h->xn, s.wk, k_loc, L, D, s.gk, h->rope, n));
@@ -499,6 +552,14 @@ int g3c_dit_create(const g3c_dit_config* cfg, g3c_dit_t** out) {
 }
 
 static void free_cp_region(g3c_dit* h) {
+  // queued peer copies / flag writes may still target these mappings (denoise_step is asynchronous): drain this device
+  // before unmapping.  The cross-rank half of the hazard (peers still pushing into OUR region) is closed by the caller's
+  // barrier on the cp group (gen3c_b200/dit.py::_teardown_barrier).
+  if (h->cp_region || h->cfg_region) cudaDeviceSynchronize();
+  if (h->cfg_peer) cudaIpcCloseMemHandle(h->cfg_peer);
+  h->cfg_peer = nullptr;
+  if (h->cfg_region) cudaFree(h->cfg_region);
+  h->cfg_region = nullptr;
   for (int r = 0; r < 8; ++r) {
     if (h->peer_base[r] && h->peer_base[r] != h->cp_region) cudaIpcCloseMemHandle(h->peer_base[r]);
     h->peer_base[r] = nullptr;
@@ -516,6 +577,7 @@ static void free_ws(g3c_dit* h) {
   h->ws_bytes = 0;
   h->L = 0;
   h->tables_ready = false;
+  h->mods_valid = false;
 }
 
 int g3c_dit_destroy(g3c_dit_t* h) {
@@ -526,6 +588,7 @@ int g3c_dit_destroy(g3c_dit_t* h) {
   if (h->comm && nccl().ok) nccl().CommDestroy(h->comm);
   if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   if (h->seq_ring) cudaFreeHost(h->seq_ring);
+  if (h->wait_ns) cudaFree(h->wait_ns);
   if (h->ev_kv) cudaEventDestroy(h->ev_kv);
   if (h->ev_gathered) cudaEventDestroy(h->ev_gathered);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -542,6 +605,7 @@ int g3c_dit_load(g3c_dit_t* h, const char* name, const void* ptr, const int64_t*
   h->w[name] = t;
   h->resolved = false;
   h->tables_ready = false;
+  h->mods_valid = false;
   return G3C_OK;
 }
 
@@ -699,6 +763,22 @@ int g3c_dit_set_shape(g3c_dit_t* h, int T_local, int H_latent, int W_latent, int
     h->peer_base[h->cp_rank] = h->cp_region;
     h->ws_bytes += h->cp_region_bytes;
   }
+  if (h->cfg_role >= 0) {
+    h->cfg_slot_bytes = align_up(lat * 2, 1024);
+    e = cudaMalloc(&h->cfg_region, 2 * h->cfg_slot_bytes + 1024);
+    if (e != cudaSuccess) {
+      h->cfg_region = nullptr;
+      set_error("dit_set_shape: cudaMalloc of the CFG exchange region failed: %s", cudaGetErrorString(e));
+      return G3C_ENOMEM;
+    }
+    G3C_CUDA(cudaMemset(h->cfg_region, 0, 2 * h->cfg_slot_bytes + 1024));
+    h->ws_bytes += 2 * h->cfg_slot_bytes + 1024;
+    h->cfg_seq = 0;
+  }
+  if (!h->wait_ns) {
+    G3C_CUDA(cudaMalloc(&h->wait_ns, sizeof(unsigned long long)));
+    G3C_CUDA(cudaMemset(h->wait_ns, 0, sizeof(unsigned long long)));
+  }
   h->T = T_local;
   h->Hl = H_latent;
   h->Wl = W_latent;
@@ -727,18 +807,89 @@ int g3c_denoise_step(g3c_dit_t* h, const g3c_step_args* a, void* stream) {
   // t = 0.25 * ln(sigma)  (EDMEulerScheduler timesteps; model_v2w.py:131-140)
   // ... fed to the net as a bf16 tensor (model_v2w.py:140 `t.to(**self.tensor_kwargs)`)
   const float timestep = __bfloat162float(__float2bfloat16_rn(0.25f * logf(a->sigma)));
+  const void* mask_u = a->cond_mask_uncond ? a->cond_mask_uncond : a->cond_mask;
   TRY(sampler_pre((const __nv_bfloat16*)a->xt, (const __nv_bfloat16*)a->gt_latent, a->aug_noise,
                   a->indicator, 16, h->T, plane, a->sigma, a->sigma_aug, a->sigma_data, h->lat_xtilde,
                   h->lat_xin, st));
-  TRY(g3c::forward(h, h->lat_xin, a->cond_mask, a->pose_cond, a->padding_mask, timestep, a->ctx_cond,
-                   h->lat_oc, st));
-  int n1 = h->launches;
-  TRY(g3c::forward(h, h->lat_xin, a->cond_mask, nullptr, a->padding_mask, timestep, a->ctx_uncond,
-                   h->lat_ou, st));
-  TRY(sampler_post(h->lat_xtilde, h->lat_oc, h->lat_ou, (const __nv_bfloat16*)a->gt_latent, a->indicator,
-                   16, h->T, plane, a->guidance, a->sigma, a->sigma_next, a->sigma_aug, a->sigma_data,
-                   (__nv_bfloat16*)a->xt_next, st));
-  h->launches += n1 + 2;
+  const __nv_bfloat16 *oc = h->lat_oc, *ou = h->lat_ou;
+  int n_launch = 2;
+  if (h->cfg_role < 0) {
+    TRY(g3c::forward(h, h->lat_xin, a->cond_mask, a->pose_cond, a->padding_mask, timestep, a->ctx_cond,
+                     h->lat_oc, st));
+    n_launch += h->launches;
+    TRY(g3c::forward(h, h->lat_xin, mask_u, nullptr, a->padding_mask, timestep, a->ctx_uncond, h->lat_ou, st));
+    n_launch += h->launches;
+  } else {
+    // CFG-parallel: this rank evaluates one branch, the partner the other; the two outputs are swapped through peer
+    // memory (copy engine push + system-scope flag), then both ranks apply the same sampler update.
+    G3C_REQUIRE(h->cfg_region && h->cfg_peer, "denoise_step: CFG partner not imported (g3c_dit_cfg_import)");
+    __nv_bfloat16* mine = h->cfg_role == 0 ? h->lat_oc : h->lat_ou;
+    if (h->cfg_role == 0)
+      TRY(g3c::forward(h, h->lat_xin, a->cond_mask, a->pose_cond, a->padding_mask, timestep, a->ctx_cond, mine, st));
+    else
+      TRY(g3c::forward(h, h->lat_xin, mask_u, nullptr, a->padding_mask, timestep, a->ctx_uncond, mine, st));
+    n_launch += h->launches;
+    const uint32_t seq = ++h->cfg_seq;
+    const int slot = seq & 1;
+    const size_t bytes = (size_t)16 * h->T * plane * 2;
+    char* peer = (char*)h->cfg_peer;
+    char* own = (char*)h->cfg_region;
+    TRY(prof_mark(h, CAT_COMM, true, st));
+    G3C_CUDA(cudaMemcpyAsync(peer + (size_t)slot * h->cfg_slot_bytes, mine, bytes, cudaMemcpyDeviceToDevice, st));
+    PeerDst pf;
+    pf.ptr[pf.n++] = peer + 2 * h->cfg_slot_bytes + (size_t)slot * 4;
+    k_cp_signal<<<1, 32, 0, st>>>(pf, seq);
+    k_wait_flag<<<1, 32, 0, st>>>((const uint32_t*)(own + 2 * h->cfg_slot_bytes) + slot, seq, peer_timeout_ns());
+    G3C_CUDA(cudaGetLastError());
+    TRY(prof_mark(h, CAT_COMM, false, st));
+    n_launch += 2;
+    const __nv_bfloat16* theirs = (const __nv_bfloat16*)(own + (size_t)slot * h->cfg_slot_bytes);
+    oc = h->cfg_role == 0 ? mine : theirs;
+    ou = h->cfg_role == 0 ? theirs : mine;
+  }
+  TRY(sampler_post(h->lat_xtilde, oc, ou, (const __nv_bfloat16*)a->gt_latent, a->indicator, 16, h->T, plane,
+                   a->guidance, a->sigma, a->sigma_next, a->sigma_aug, a->sigma_data, (__nv_bfloat16*)a->xt_next,
+                   (__nv_bfloat16*)a->net_output, st));
+  h->launches = n_launch;
+  return G3C_OK;
+}
+
+int g3c_dit_enable_cfg_parallel(g3c_dit_t* h, int role) {
+  G3C_REQUIRE(h && role <= 1, "enable_cfg_parallel: role must be 0 (cond), 1 (uncond) or negative (off)");
+  h->cfg_role = role < 0 ? -1 : role;
+  free_ws(h);  // the exchange region is allocated with the shape
+  return G3C_OK;
+}
+
+int g3c_dit_cfg_export(g3c_dit_t* h, void* out_handle64) {
+  G3C_REQUIRE(h && out_handle64, "cfg_export: null argument");
+  G3C_REQUIRE(h->cfg_region, "cfg_export: no exchange region (enable_cfg_parallel, then set_shape)");
+  cudaIpcMemHandle_t hd;
+  G3C_CUDA(cudaIpcGetMemHandle(&hd, h->cfg_region));
+  memcpy(out_handle64, &hd, 64);
+  return G3C_OK;
+}
+
+int g3c_dit_cfg_import(g3c_dit_t* h, const void* partner_handle64) {
+  G3C_REQUIRE(h && partner_handle64, "cfg_import: null argument");
+  G3C_REQUIRE(h->cfg_region, "cfg_import: no exchange region");
+  if (h->cfg_peer) return G3C_OK;
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, partner_handle64, 64);
+  G3C_CUDA(cudaIpcOpenMemHandle(&h->cfg_peer, hd, cudaIpcMemLazyEnablePeerAccess));
+  return G3C_OK;
+}
+
+int g3c_dit_profile_wait_ms(g3c_dit_t* h, float* ms) {
+  G3C_REQUIRE(h && ms, "dit_profile_wait_ms: null argument");
+  *ms = 0.f;
+  if (!h->wait_ns) return G3C_OK;
+  unsigned long long v = 0;
+  G3C_CUDA(cudaDeviceSynchronize());
+  G3C_CUDA(cudaMemcpy(&v, h->wait_ns, sizeof(v), cudaMemcpyDeviceToHost));
+  G3C_CUDA(cudaMemset(h->wait_ns, 0, sizeof(v)));
+  // total ns over all CTAs and launches / CTAs per launch = sum over launches of the mean wait per CTA
+  if (h->wait_cta_launches > 0) *ms = (float)((double)v * 1e-6 / h->wait_cta_launches);
   return G3C_OK;
 }
 
@@ -747,6 +898,7 @@ int g3c_dit_profile(g3c_dit_t* h, int enable) {
   h->prof = enable != 0;
   h->ev_used = 0;
   h->ev_cat.clear();
+  if (h->wait_ns) G3C_CUDA(cudaMemset(h->wait_ns, 0, sizeof(unsigned long long)));
   return G3C_OK;
 }
 

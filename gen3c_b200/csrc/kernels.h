@@ -29,7 +29,9 @@ struct ChunkGate {
   const uint32_t* flags = nullptr;
   uint32_t seq = 0;
   int first = 0;
+  unsigned long long* wait_ns = nullptr;  // optional: += ns each CTA's loader spent polling flags (profiling)
 };
+unsigned long long peer_timeout_ns();  // bound of inter-process waits (G3C_PEER_TIMEOUT_S, default 600 s)
 int attn_fwd(const void* q, const void* k, const void* vt, void* o, int Lq, int Lk, int heads,
              int ldq, int ldk, int ldo, int vt_chunk_len, float scale, cudaStream_t st,
              const ChunkGate* gate = nullptr);
@@ -61,6 +63,6 @@ int sampler_pre(const __nv_bfloat16* xt, const __nv_bfloat16* gt, const float* n
 int sampler_post(const __nv_bfloat16* xtilde, const __nv_bfloat16* oc, const __nv_bfloat16* ou,
                  const __nv_bfloat16* gt, const float* ind_t, int C, int T, size_t plane, float guidance,
                  float sigma, float sigma_next, float sigma_aug, float sd, __nv_bfloat16* xnext,
-                 cudaStream_t st);
+                 __nv_bfloat16* net_out, cudaStream_t st);
 
 }  // namespace g3c

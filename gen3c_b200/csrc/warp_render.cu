@@ -99,9 +99,11 @@ struct ItemMap {
   int N;          // buffers per camera
   int F;          // cameras (target frames) per batch element
   int src_bcast;  // 1: cache has a single frame broadcast over F targets
-  __device__ __forceinline__ int cam(int i) const { return i / N; }
+  int item0;      // first item of the current pass (foreground pass: blockIdx.y counts from here)
+  __device__ __forceinline__ int cam(int i) const { return (i + item0) / N; }
   __device__ __forceinline__ int src(int i) const {
-    return src_bcast ? (i / (N * F)) * N + (i % N) : i;
+    const int j = i + item0;
+    return src_bcast ? (j / (N * F)) * N + (j % N) : j;
   }
 };
 
@@ -424,12 +426,12 @@ __device__ __forceinline__ AxisTap bilinear_tap(int dst, int n_in, int n_out) {
 // the nearest-resampled boundary mask.  verts [item][nh][nw][3], vmask [item][nh][nw]
 __global__ void __launch_bounds__(256)
     k_fg_mesh_points(const float* __restrict__ points, const uint8_t* __restrict__ boundary,
-                     const float* __restrict__ w2c, int H, int W, int nh, int nw, float* __restrict__ verts,
+                     const float* __restrict__ w2c, ItemMap map, int H, int W, int nh, int nw, float* __restrict__ verts,
                      uint8_t* __restrict__ vmask) {
   const int item = blockIdx.y;
-  const float* m = w2c + 16 * item;
-  const float* p = points + (size_t)item * H * W * 3;
-  const uint8_t* bm = boundary + (size_t)item * H * W;
+  const float* m = w2c + 16 * map.cam(item);
+  const float* p = points + (size_t)map.src(item) * H * W * 3;
+  const uint8_t* bm = boundary + (size_t)map.src(item) * H * W;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nh * nw; i += gridDim.x * blockDim.x) {
     const int vy = i / nw, vx = i - vy * nw;
     const AxisTap ty = bilinear_tap(vy, H, nh), tx = bilinear_tap(vx, W, nw);
@@ -499,10 +501,10 @@ __device__ __forceinline__ float ray_tri(const Ray& d, const float* v0, const fl
 // one thread per mesh patch (u, v): its two triangles (tl, tr, bl) and (tr, br, bl) when any corner is on the boundary
 __global__ void __launch_bounds__(256)
     k_fg_raster(const float* __restrict__ verts, const uint8_t* __restrict__ vmask, const float* __restrict__ K,
-                const float* __restrict__ Kinv, int H, int W, int nh, int nw, uint32_t* __restrict__ tbuf) {
+                const float* __restrict__ Kinv, ItemMap map, int H, int W, int nh, int nw, uint32_t* __restrict__ tbuf) {
   const int item = blockIdx.y;
-  const float* k = K + 9 * item;
-  const float* kinv = Kinv + 9 * item;
+  const float* k = K + 9 * map.cam(item);
+  const float* kinv = Kinv + 9 * map.cam(item);
   const float* vb = verts + (size_t)item * nh * nw * 3;
   const uint8_t* mb = vmask + (size_t)item * nh * nw;
   uint32_t* tb = tbuf + (size_t)item * H * W;
@@ -547,11 +549,11 @@ __global__ void __launch_bounds__(256)
 // :317-334: mesh z-depth = t * ray_z (the bilinear resample to the same size is the identity), pixels whose mesh depth
 // is more than 0.02 in front of the splatted depth are removed from mask / image (fill -1) / depth
 __global__ void __launch_bounds__(256)
-    k_fg_apply(const uint32_t* __restrict__ tbuf, const float* __restrict__ Kinv, int C, int H, int W,
+    k_fg_apply(const uint32_t* __restrict__ tbuf, const float* __restrict__ Kinv, ItemMap map, int C, int H, int W,
                float* __restrict__ warped, float* __restrict__ mask, float* __restrict__ depth) {
   const int item = blockIdx.y;
   const int HW = H * W;
-  const float* kinv = Kinv + 9 * item;
+  const float* kinv = Kinv + 9 * map.cam(item);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
     const uint32_t bits = tbuf[(size_t)item * HW + i];
     if (bits >= 0x7F800000u) continue;  // no hit (initialised to 0xFFFFFFFF)
@@ -570,6 +572,113 @@ __global__ void __launch_bounds__(256)
 __global__ void k_fg_invert_k(const float* __restrict__ K, int n, float* __restrict__ Kinv) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) invert_small(K + 9 * i, 3, Kinv + 9 * i);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Non-rigid depth alignment of Cache3D_Buffer.update_cache (reference camera_utils.py:292-345):
+// a per-pixel scale map sc, num_iters Adam steps on
+//     mean_{p in mask, c} | (R (d_p sc_p r_p) + t)_c - (R (t_p r_p) + t)_c |  +  lambda * mean_p | box3(sc)_p - sc_p |
+// The reference runs 100 x (unproject_points twice + autograd + torch.optim.Adam) = ~4 000 ATen launches; the gradient
+// is closed form (sign(d_p sc_p - t_p) d_p |R r_p|_1 / 3n  +  lambda (box3(g) - g)/HW, g = sign(box3(sc) - sc)), so one
+// stencil kernel per iteration does loss gradient + Adam update.  HBM/L2-resident: 28 B/px per iteration.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_align_setup(const float* __restrict__ K, const float* __restrict__ c2w, float* __restrict__ mats) {
+  // mats[0..8] = K^-1, mats[9..17] = rotation of inverse(c2w) (unproject_points inverts the matrix it is given)
+  if (threadIdx.x == 0) {
+    float kinv[9], w2c[16];
+    invert_small(K, 3, kinv);
+    invert_small(c2w, 4, w2c);
+    for (int i = 0; i < 9; ++i) mats[i] = kinv[i];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) mats[9 + 3 * r + c] = w2c[4 * r + c];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    k_align_count(const uint8_t* __restrict__ mask, int HW, unsigned int* __restrict__ count) {
+  unsigned int n = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) n += mask[i] ? 1u : 0u;
+  n = __reduce_add_sync(0xffffffffu, n);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(count, n);
+}
+
+// coef_p = mask_p ? d_p |R K^-1 (x,y,1)|_1 / (3 n) : 0 ; sc = 1 ; Adam moments = 0
+__global__ void __launch_bounds__(256)
+    k_align_init(const float* __restrict__ depth, const uint8_t* __restrict__ mask, const float* __restrict__ mats,
+                 const unsigned int* __restrict__ count, int H, int W, float* __restrict__ coef, float* __restrict__ sc,
+                 float* __restrict__ m1, float* __restrict__ m2) {
+  const float inv3n = 1.0f / (3.0f * (float)max(*count, 1u));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * W; i += gridDim.x * blockDim.x) {
+    const int y = i / W, x = i - y * W;
+    const float fx = (float)x, fy = (float)y;
+    const float rx = __fadd_rn(__fmaf_rn(mats[1], fy, __fmul_rn(mats[0], fx)), mats[2]);
+    const float ry = __fadd_rn(__fmaf_rn(mats[4], fy, __fmul_rn(mats[3], fx)), mats[5]);
+    const float rz = __fadd_rn(__fmaf_rn(mats[7], fy, __fmul_rn(mats[6], fx)), mats[8]);
+    float l1 = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) l1 += fabsf(mats[9 + 3 * r] * rx + mats[10 + 3 * r] * ry + mats[11 + 3 * r] * rz);
+    coef[i] = mask[i] ? depth[i] * l1 * inv3n : 0.0f;
+    sc[i] = 1.0f;
+    m1[i] = 0.0f;
+    m2[i] = 0.0f;
+  }
+}
+
+__device__ __forceinline__ float sign_f(float v) { return v > 0.0f ? 1.0f : (v < 0.0f ? -1.0f : 0.0f); }
+
+constexpr int AL_TX = 32, AL_TY = 8;
+__global__ void __launch_bounds__(AL_TX * AL_TY)
+    k_align_step(const float* __restrict__ depth, const float* __restrict__ target, const float* __restrict__ coef,
+                 const float* __restrict__ sc_in, float* __restrict__ sc_out, float* __restrict__ m1,
+                 float* __restrict__ m2, int H, int W, float arap_w, float step_size, float bc2_sqrt) {
+  __shared__ float s_sc[AL_TY + 4][AL_TX + 4];
+  __shared__ float s_g[AL_TY + 2][AL_TX + 2];
+  const int x0 = blockIdx.x * AL_TX, y0 = blockIdx.y * AL_TY;
+  const int tid = threadIdx.y * AL_TX + threadIdx.x;
+  for (int i = tid; i < (AL_TY + 4) * (AL_TX + 4); i += AL_TX * AL_TY) {
+    const int ly = i / (AL_TX + 4), lx = i - ly * (AL_TX + 4);
+    const int y = y0 + ly - 2, x = x0 + lx - 2;
+    s_sc[ly][lx] = (y >= 0 && y < H && x >= 0 && x < W) ? sc_in[(size_t)y * W + x] : 0.0f;  // conv2d zero padding
+  }
+  __syncthreads();
+  const float ninth = 1.0f / 9.0f;
+  for (int i = tid; i < (AL_TY + 2) * (AL_TX + 2); i += AL_TX * AL_TY) {
+    const int ly = i / (AL_TX + 2), lx = i - ly * (AL_TX + 2);
+    const int y = y0 + ly - 1, x = x0 + lx - 1;
+    float g = 0.0f;
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      float sm = 0.0f;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) sm = __fmaf_rn(s_sc[ly + dy][lx + dx], ninth, sm);
+      g = sign_f(sm - s_sc[ly + 1][lx + 1]);
+    }
+    s_g[ly][lx] = g;
+  }
+  __syncthreads();
+  const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+  if (x >= W || y >= H) return;
+  const size_t p = (size_t)y * W + x;
+  float bg = 0.0f;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) bg = __fmaf_rn(s_g[threadIdx.y + dy][threadIdx.x + dx], ninth, bg);
+  const float sc = s_sc[threadIdx.y + 2][threadIdx.x + 2];
+  const float e = depth[p] * sc - target[p];
+  const float grad = coef[p] * sign_f(e) + arap_w * (bg - s_g[threadIdx.y + 1][threadIdx.x + 1]);
+  // torch.optim.Adam (betas .9/.999, eps 1e-8, no weight decay)
+  const float a = 0.9f * m1[p] + 0.1f * grad;
+  const float b = 0.999f * m2[p] + 0.001f * grad * grad;
+  m1[p] = a;
+  m2[p] = b;
+  sc_out[p] = sc - step_size * a / (sqrtf(b) / bc2_sqrt + 1e-8f);
+}
+
+__global__ void __launch_bounds__(256)
+    k_align_finish(const float* __restrict__ depth, const float* __restrict__ sc, int HW, float* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) out[i] = depth[i] * sc[i];
 }
 
 static inline dim3 px_grid(int HW, int items) {
@@ -648,7 +757,7 @@ int g3c_forward_warp(g3c_render_t* r, const float* points, const float* image, c
               "forward_warp: null argument");
   int want_depth = (flags & G3C_WARP_RENDER_DEPTH) != 0;
   G3C_REQUIRE(!want_depth || depth_out, "forward_warp: render_depth set but depth_out is NULL");
-  ItemMap map{1, b, 0};
+  ItemMap map{1, b, 0, 0};
   return render_items(r, points, image, mask, w2c, K, map, b, C, /*group=*/b,
                       (flags & G3C_WARP_NOT_IMAGE) ? 0 : 1, want_depth, warped, mask_out, depth_out,
                       flow_out, (cudaStream_t)stream);
@@ -664,7 +773,7 @@ int g3c_render_cache(g3c_render_t* r, const float* points, const float* images, 
               "render_cache: cache has %d frames, targets %d (must be 1 or equal)", src_frames,
               F_target);
   G3C_REQUIRE(!render_depth || depth_out, "render_cache: render_depth set but depth_out is NULL");
-  ItemMap map{N, F_target, src_frames == 1 ? 1 : 0};
+  ItemMap map{N, F_target, src_frames == 1 ? 1 : 0, 0};
   return render_items(r, points, images, masks, w2cs, Ks, map, B * F_target * N, 3,
                       /*group=*/2, 1, render_depth, pixels, masks_out, depth_out, nullptr,
                       (cudaStream_t)stream);
@@ -719,31 +828,86 @@ int g3c_reliable_depth_mask(const float* depth, int b, int H, int W, int window,
   return G3C_OK;
 }
 
-int g3c_foreground_occlusion(const float* points, const uint8_t* boundary, const float* w2c, const float* K, int b, int C,
-                             int H, int W, float* warped, float* mask, float* depth, void* stream) {
-  G3C_REQUIRE(points && boundary && w2c && K && warped && mask && depth, "foreground_occlusion: null argument");
-  G3C_REQUIRE(b > 0 && b <= 65535 && C >= 1 && C <= 3 && H >= 8 && W >= 8, "foreground_occlusion: bad sizes");
+int g3c_align_depth_nonrigid(const float* depth, const float* target_depth, const uint8_t* target_mask, const float* K,
+                             const float* c2w, int H, int W, int num_iters, float lambda_arap, float lr, float* out_depth,
+                             void* stream) {
+  G3C_REQUIRE(depth && target_depth && target_mask && K && c2w && out_depth, "align_depth_nonrigid: null argument");
+  G3C_REQUIRE(H > 0 && W > 0 && num_iters >= 0 && lr > 0, "align_depth_nonrigid: bad sizes");
   cudaStream_t st = (cudaStream_t)stream;
+  const size_t HW = (size_t)H * W;
+  float* buf = nullptr;  // coef | sc0 | sc1 | m1 | m2 | mats(18) | count
+  G3C_CUDA(cudaMallocAsync(&buf, (5 * HW + 32) * sizeof(float), st));
+  float *coef = buf, *sc0 = buf + HW, *sc1 = buf + 2 * HW, *m1 = buf + 3 * HW, *m2 = buf + 4 * HW, *mats = buf + 5 * HW;
+  unsigned int* count = reinterpret_cast<unsigned int*>(mats + 24);
+  G3C_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned int), st));
+  k_align_setup<<<1, 32, 0, st>>>(K, c2w, mats);
+  k_align_count<<<px_grid((int)HW, 1), 256, 0, st>>>(target_mask, (int)HW, count);
+  k_align_init<<<px_grid((int)HW, 1), 256, 0, st>>>(depth, target_mask, mats, count, H, W, coef, sc0, m1, m2);
+  const dim3 grid((W + AL_TX - 1) / AL_TX, (H + AL_TY - 1) / AL_TY), block(AL_TX, AL_TY);
+  float *cur = sc0, *nxt = sc1;
+  for (int it = 1; it <= num_iters; ++it) {
+    const float step = (float)((double)lr / (1.0 - pow(0.9, (double)it)));
+    const float bc2 = (float)sqrt(1.0 - pow(0.999, (double)it));
+    k_align_step<<<grid, block, 0, st>>>(depth, target_depth, coef, cur, nxt, m1, m2, H, W,
+                                         lambda_arap / (float)HW, step, bc2);
+    float* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+  k_align_finish<<<px_grid((int)HW, 1), 256, 0, st>>>(depth, cur, (int)HW, out_depth);
+  G3C_CUDA(cudaGetLastError());
+  G3C_CUDA(cudaFreeAsync(buf, st));
+  return G3C_OK;
+}
+
+static int foreground_items(const float* points, const uint8_t* boundary, const float* w2c, const float* K, ItemMap map,
+                            int n_cam, int n_items, int C, int H, int W, float* warped, float* mask, float* depth,
+                            cudaStream_t st) {
   const int nh = H / 4, nw = W / 4;  // mesh_downsample_factor = 4 (:289)
-  const size_t nv = (size_t)b * nh * nw;
   float *verts = nullptr, *kinv = nullptr;
   uint8_t* vmask = nullptr;
   uint32_t* tbuf = nullptr;
-  G3C_CUDA(cudaMallocAsync(&verts, nv * 3 * sizeof(float), st));
-  G3C_CUDA(cudaMallocAsync(&vmask, nv, st));
-  G3C_CUDA(cudaMallocAsync(&kinv, (size_t)b * 9 * sizeof(float), st));
-  G3C_CUDA(cudaMallocAsync(&tbuf, (size_t)b * H * W * sizeof(uint32_t), st));
-  G3C_CUDA(cudaMemsetAsync(tbuf, 0xFF, (size_t)b * H * W * sizeof(uint32_t), st));
-  k_fg_invert_k<<<(b + 63) / 64, 64, 0, st>>>(K, b, kinv);
-  k_fg_mesh_points<<<px_grid(nh * nw, b), 256, 0, st>>>(points, boundary, w2c, H, W, nh, nw, verts, vmask);
-  k_fg_raster<<<px_grid((nh - 1) * (nw - 1), b), 256, 0, st>>>(verts, vmask, K, kinv, H, W, nh, nw, tbuf);
-  k_fg_apply<<<px_grid(H * W, b), 256, 0, st>>>(tbuf, kinv, C, H, W, warped, mask, depth);
+  G3C_CUDA(cudaMallocAsync(&kinv, (size_t)n_cam * 9 * sizeof(float), st));
+  k_fg_invert_k<<<(n_cam + 63) / 64, 64, 0, st>>>(K, n_cam, kinv);
+  // items in passes of <= 64 frames: bounds the scratch (verts, t-buffer) at full resolution
+  const int pass = n_items < 64 ? n_items : 64;
+  G3C_CUDA(cudaMallocAsync(&verts, (size_t)pass * nh * nw * 3 * sizeof(float), st));
+  G3C_CUDA(cudaMallocAsync(&vmask, (size_t)pass * nh * nw, st));
+  G3C_CUDA(cudaMallocAsync(&tbuf, (size_t)pass * H * W * sizeof(uint32_t), st));
+  for (int i0 = 0; i0 < n_items; i0 += pass) {
+    const int n = n_items - i0 < pass ? n_items - i0 : pass;
+    ItemMap m = map;
+    m.item0 = i0;
+    G3C_CUDA(cudaMemsetAsync(tbuf, 0xFF, (size_t)n * H * W * sizeof(uint32_t), st));
+    k_fg_mesh_points<<<px_grid(nh * nw, n), 256, 0, st>>>(points, boundary, w2c, m, H, W, nh, nw, verts, vmask);
+    k_fg_raster<<<px_grid((nh - 1) * (nw - 1), n), 256, 0, st>>>(verts, vmask, K, kinv, m, H, W, nh, nw, tbuf);
+    k_fg_apply<<<px_grid(H * W, n), 256, 0, st>>>(tbuf, kinv, m, C, H, W, warped + (size_t)i0 * C * H * W,
+                                                  mask + (size_t)i0 * H * W, depth + (size_t)i0 * H * W);
+  }
   G3C_CUDA(cudaGetLastError());
   G3C_CUDA(cudaFreeAsync(verts, st));
   G3C_CUDA(cudaFreeAsync(vmask, st));
   G3C_CUDA(cudaFreeAsync(kinv, st));
   G3C_CUDA(cudaFreeAsync(tbuf, st));
   return G3C_OK;
+}
+
+int g3c_foreground_occlusion(const float* points, const uint8_t* boundary, const float* w2c, const float* K, int b, int C,
+                             int H, int W, float* warped, float* mask, float* depth, void* stream) {
+  G3C_REQUIRE(points && boundary && w2c && K && warped && mask && depth, "foreground_occlusion: null argument");
+  G3C_REQUIRE(b > 0 && C >= 1 && C <= 3 && H >= 8 && W >= 8, "foreground_occlusion: bad sizes");
+  return foreground_items(points, boundary, w2c, K, ItemMap{1, b, 0, 0}, b, b, C, H, W, warped, mask, depth,
+                          (cudaStream_t)stream);
+}
+
+int g3c_render_cache_occlusion(const float* points, const uint8_t* boundary, const float* w2cs, const float* Ks, int B,
+                               int F_target, int N, int src_frames, float* pixels, float* masks, float* depth,
+                               int H, int W, void* stream) {
+  G3C_REQUIRE(points && boundary && w2cs && Ks && pixels && masks && depth, "render_cache_occlusion: null argument");
+  G3C_REQUIRE(B > 0 && F_target > 0 && N > 0 && (src_frames == 1 || src_frames == F_target) && H >= 8 && W >= 8,
+              "render_cache_occlusion: bad sizes");
+  return foreground_items(points, boundary, w2cs, Ks, ItemMap{N, F_target, src_frames == 1 ? 1 : 0, 0}, B * F_target,
+                          B * F_target * N, 3, H, W, pixels, masks, depth, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -95,6 +95,7 @@ class VideoExtendGeneralDIT(nn.Module):
         self.base_fps = base_fps
         self.patch_spatial, self.patch_temporal = patch_spatial, patch_temporal
         self.cp_group = None
+        self.cfg_group = None
         self._handle = None
         self._registered_ptrs = None
         self._shape_key = None
@@ -154,7 +155,10 @@ class VideoExtendGeneralDIT(nn.Module):
         lib = _lib.load()
         h = self._engine()
         params = [(k, v) for k, v in self.state_dict(keep_vars=True).items() if k != "pos_embedder.seq"]
-        ptrs = tuple(v.data_ptr() for _, v in params)
+        # (address, version counter): an in-place update (load_state_dict, param.copy_) keeps the address but bumps
+        # the version; the engine caches derived copies (padded patch-embed weight, fp32 RMSNorm gains, abs-pos table,
+        # modulation vectors) that g3c_dit_load invalidates
+        ptrs = tuple((v.data_ptr(), v._version) for _, v in params)
         if ptrs == self._registered_ptrs:
             return
         for k, v in params:
@@ -168,18 +172,30 @@ class VideoExtendGeneralDIT(nn.Module):
         key = (T, H, W, ctx_len, fps)
         if key != self._shape_key:
             lib = _lib.load()
+            if self._shape_key is not None:
+                self._teardown_barrier()  # a live peer-mapped region is about to be freed
             _lib.check(lib.g3c_dit_set_shape(self._engine(), T, H, W, ctx_len, fps), "g3c_dit_set_shape")
             if self.cp_group is not None and lib.g3c_dit_cp_mode(self._engine()) == 1:
-                # fused peer-memory mode: exchange the IPC handles of the per-rank K / V^T regions (collective)
+                # fused peer-memory mode: exchange the IPC handles of the per-rank K / V^T regions (collective; plain
+                # python objects, so any torch.distributed backend will do)
                 import torch.distributed as dist
 
                 buf = (C.c_uint8 * 64)()
                 _lib.check(lib.g3c_dit_cp_export(self._engine(), buf), "g3c_dit_cp_export")
-                mine = torch.tensor(list(buf), dtype=torch.uint8, device="cuda")
-                allh = [torch.empty_like(mine) for _ in range(self._cp_size)]
-                dist.all_gather(allh, mine, group=self.cp_group)
-                raw = bytes(torch.cat(allh).cpu().tolist())
-                _lib.check(lib.g3c_dit_cp_import(self._engine(), raw, self._cp_size), "g3c_dit_cp_import")
+                allh = [None] * self._cp_size
+                dist.all_gather_object(allh, bytes(buf), group=self.cp_group)
+                _lib.check(lib.g3c_dit_cp_import(self._engine(), b"".join(allh), self._cp_size), "g3c_dit_cp_import")
+                # every rank has resolved, allocated and mapped before anyone launches a kernel that polls a peer flag
+                dist.barrier(group=self.cp_group)
+            if self.cfg_group is not None:
+                import torch.distributed as dist
+
+                buf = (C.c_uint8 * 64)()
+                _lib.check(lib.g3c_dit_cfg_export(self._engine(), buf), "g3c_dit_cfg_export")
+                both = [None, None]
+                dist.all_gather_object(both, bytes(buf), group=self.cfg_group)
+                _lib.check(lib.g3c_dit_cfg_import(self._engine(), both[1 - self._cfg_role]), "g3c_dit_cfg_import")
+                dist.barrier(group=self.cfg_group)
             self._shape_key = key
 
     def __del__(self):
@@ -204,6 +220,7 @@ class VideoExtendGeneralDIT(nn.Module):
         import torch.distributed as dist
 
         mode = mode or os.environ.get("G3C_CP_MODE", "p2p")
+        self._teardown_barrier()
         rank, size = dist.get_rank(cp_group), dist.get_world_size(cp_group)
         lib = _lib.load()
         raw = None
@@ -223,9 +240,49 @@ class VideoExtendGeneralDIT(nn.Module):
         self._shape_key = None
 
     def disable_context_parallel(self):
+        self._teardown_barrier()
         if self._handle is not None:
             _lib.check(_lib.load().g3c_dit_disable_cp(self._handle), "g3c_dit_disable_cp")
         self.cp_group = None
+        self._shape_key = None
+
+    def _teardown_barrier(self):
+        """Before peer-mapped regions are unmapped / freed: this rank's queued work is done and so is every peer's
+        (they may still be pushing K / V^T or CFG outputs into the region this rank is about to free)."""
+        if self._shape_key is None or (self.cp_group is None and self.cfg_group is None):
+            return
+        import torch.distributed as dist
+
+        torch.cuda.synchronize()
+        for g in (self.cp_group, self.cfg_group):
+            if g is not None:
+                dist.barrier(group=g)
+
+    # ------------------------------------------------------------------------------------------
+    # classifier-free-guidance parallelism (extension; SURVEY.md §8e "CFG x CP hybrid")
+    # ------------------------------------------------------------------------------------------
+    @property
+    def is_cfg_parallel_enabled(self) -> bool:
+        return self.cfg_group is not None
+
+    def enable_cfg_parallel(self, cfg_group):
+        """`cfg_group`: a 2-rank process group; group rank 0 evaluates the conditional forward of every denoise step,
+        rank 1 the unconditional one, and `sampler.denoise_step` swaps the two network outputs over NVLink peer memory.
+        Both ranks must hold the same latent slice (same context-parallel rank in their respective cp groups)."""
+        import torch.distributed as dist
+
+        assert dist.get_world_size(cfg_group) == 2, "a CFG pair has exactly two ranks"
+        self._teardown_barrier()
+        self._cfg_role = dist.get_rank(cfg_group)
+        _lib.check(_lib.load().g3c_dit_enable_cfg_parallel(self._engine(), self._cfg_role), "g3c_dit_enable_cfg_parallel")
+        self.cfg_group = cfg_group
+        self._shape_key = None
+
+    def disable_cfg_parallel(self):
+        self._teardown_barrier()
+        if self._handle is not None:
+            _lib.check(_lib.load().g3c_dit_enable_cfg_parallel(self._handle, -1), "g3c_dit_enable_cfg_parallel")
+        self.cfg_group = None
         self._shape_key = None
 
     def _cp_slice(self, t: Optional[torch.Tensor], dim: int = 2) -> Optional[torch.Tensor]:

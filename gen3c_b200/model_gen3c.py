@@ -138,13 +138,20 @@ def generate_samples_from_batch(net: VideoExtendGeneralDIT, condition: VideoExte
     fps = float(condition.fps.flatten()[0]) if condition.fps is not None else 24.0
     x = loc(xt)
     gt, mask, pose = loc(condition.gt_latent), loc(condition.condition_video_input_mask), loc(condition.condition_video_pose)
+    # the unconditional branch sees uncondition's own input mask (all zeros under add_input_frames_guidance,
+    # model_v2w.py:76-80) and a zero pose (model_gen3c.py:101-104, drop_out_latent=True)
+    mask_u = loc(uncondition.condition_video_input_mask)
+    if uncondition.condition_video_pose is not None and bool(uncondition.condition_video_pose.any()):
+        raise NotImplementedError("the unconditional branch of GEN3C drops the pose latents (model_gen3c.py:103); "
+                                  "a non-zero uncondition.condition_video_pose is not supported")
     ind = condition.condition_video_indicator[0, 0, sl, 0, 0].float().contiguous()
     nz = noise[0, :, sl].contiguous()
     ctx_c = condition.crossattn_emb[0].to(bf).contiguous()
     ctx_u = uncondition.crossattn_emb[0].to(bf).contiguous()
     for i in range(num_steps):
         x = sampler.denoise_step(net, x, gt, nz, ind, mask, pose, pad, ctx_c, ctx_u, float(sch.sigmas[i]),
-                                 float(sch.sigmas[i + 1]), guidance, sigma_data, condition_augment_sigma, fps)
+                                 float(sch.sigmas[i + 1]), guidance, sigma_data, condition_augment_sigma, fps,
+                                 cond_mask_uncond=mask_u)
     samples = x[None]
     if net.is_context_parallel_enabled:
         samples = cat_outputs_cp(samples, seq_dim=2, cp_group=net.cp_group)

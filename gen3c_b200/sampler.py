@@ -50,10 +50,15 @@ def denoise_step(net: VideoExtendGeneralDIT, xt: torch.Tensor, gt_latent: torch.
                  indicator: torch.Tensor, cond_mask: torch.Tensor, pose_cond: Optional[torch.Tensor],
                  padding_mask: Optional[torch.Tensor], ctx_cond: torch.Tensor, ctx_uncond: torch.Tensor, sigma: float,
                  sigma_next: float, guidance: float, sigma_data: float = 0.5, sigma_aug: float = 0.001,
-                 fps: float = 24.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 fps: float = 24.0, out: Optional[torch.Tensor] = None,
+                 cond_mask_uncond: Optional[torch.Tensor] = None,
+                 net_output: Optional[torch.Tensor] = None) -> torch.Tensor:
     """One loop body of generate_samples_from_batch for B = 1 (this rank's T slice under CP).
     xt, gt_latent bf16 [16,T,H,W]; aug_noise f32 [16,T,H,W]; indicator f32 [T]; cond_mask bf16 [1,T,H,W];
-    pose_cond bf16 [64,T,H,W]; padding_mask bf16 [H,W] (latent resolution) or None; ctx_* bf16 [M, ctx_dim]."""
+    pose_cond bf16 [64,T,H,W]; padding_mask bf16 [H,W] (latent resolution) or None; ctx_* bf16 [M, ctx_dim].
+    cond_mask_uncond: uncondition.condition_video_input_mask when it differs from the conditional one
+    (add_input_frames_guidance, model_v2w.py:76-80); net_output: optional bf16 [16,T,H,W] receiving the CFG-combined
+    network output of model_v2w.py:143."""
     _, T, H, W = xt.shape
     net._sync_weights()
     net._set_shape(T, H, W, ctx_cond.shape[0], fps)
@@ -61,7 +66,8 @@ def denoise_step(net: VideoExtendGeneralDIT, xt: torch.Tensor, gt_latent: torch.
         out = torch.empty_like(xt)
     a = _lib.StepArgs(_lib.ptr(xt), _lib.ptr(gt_latent), _lib.ptr(aug_noise), _lib.ptr(indicator), _lib.ptr(cond_mask),
                       _lib.ptr(pose_cond), _lib.ptr(padding_mask), _lib.ptr(ctx_cond), _lib.ptr(ctx_uncond),
-                      sigma, sigma_next, sigma_data, sigma_aug, guidance, _lib.ptr(out))
+                      sigma, sigma_next, sigma_data, sigma_aug, guidance, _lib.ptr(out), _lib.ptr(cond_mask_uncond),
+                      _lib.ptr(net_output))
     with torch.cuda.device(xt.device):
         _lib.check(_lib.load().g3c_denoise_step(net._engine(), C.byref(a), _lib.stream_ptr()), "g3c_denoise_step")
     return out

@@ -6,7 +6,6 @@ function).  Tensors are CUDA float32; there is no CPU path.
 """
 from __future__ import annotations
 
-import os
 from typing import Optional, Tuple
 
 import torch
@@ -134,12 +133,7 @@ def forward_warp(
     if conditioned_normal1 is not None or cameraray_filtering:
         raise NotImplementedError("normal / camera-ray filtering is not on the GEN3C inference path")
     if foreground_masking:
-        # SURVEY.md §8(f) rank 1.  The native pass (g3c_foreground_occlusion) exists together with its CPU restatement and golden vector,
-        # but has not run on hardware yet: it stays opt-in until its GPU parity test has passed on a B200.
-        if os.environ.get("G3C_EXPERIMENTAL_FOREGROUND", "0") != "1":
-            raise NotImplementedError("foreground_masking (mesh occlusion pass, SURVEY.md §8(f) rank 1) is experimental: "
-                                      "set G3C_EXPERIMENTAL_FOREGROUND=1 to use the unvalidated native pass")
-        assert boundary_mask is not None
+        assert boundary_mask is not None  # reference :286
     b, c, h, w = frame1.shape
     if intrinsic2 is None:
         assert intrinsic1 is not None, "intrinsic2 cannot be derived if intrinsic1 is None and intrinsic2 is None"
@@ -186,22 +180,32 @@ def forward_warp(
 
 
 def render_cache(points: torch.Tensor, images: torch.Tensor, masks: Optional[torch.Tensor], w2cs: torch.Tensor,
-                 Ks: torch.Tensor, render_depth: bool = False, max_items_per_pass: int = 4):
+                 Ks: torch.Tensor, render_depth: bool = False, max_items_per_pass: int = 4,
+                 boundary_masks: Optional[torch.Tensor] = None):
     """Fused cache render (the loop of reference cache_3d.py:175-223 in one native call).
     points (B,Fs,N,H,W,3), images (B,Fs,N,3,H,W), masks (B,Fs,N,1,H,W)|None, Fs in {1,F};
-    w2cs (B,F,4,4), Ks (B,F,3,3) -> pixels (B,F,N,3,H,W) [depth (B,F,N,H,W) if render_depth], masks."""
+    w2cs (B,F,4,4), Ks (B,F,3,3) -> pixels (B,F,N,3,H,W) [depth (B,F,N,H,W) if render_depth], masks.
+    boundary_masks (B,Fs,N,H,W) bool: foreground_masking=True — the mesh occlusion pass of forward_warp :285-335 runs
+    on every item (a second native call) before the result is returned."""
     B, Fs, N, H, W, _ = points.shape
     F = w2cs.shape[1]
     dev = points.device
+    fg = boundary_masks is not None
     pix = torch.empty((B, F, N, 3, H, W), device=dev, dtype=torch.float32)
     mk = torch.empty((B, F, N, 1, H, W), device=dev, dtype=torch.float32)
-    dep = torch.empty((B, F, N, H, W), device=dev, dtype=torch.float32) if render_depth else None
+    dep = torch.empty((B, F, N, H, W), device=dev, dtype=torch.float32) if (render_depth or fg) else None
     lib = _lib.load()
     with torch.cuda.device(dev):
         ws = _workspace(H, W, dev, max_items_per_pass)
-        _lib.check(lib.g3c_render_cache(ws, _lib.ptr(_f32c(points, "points")), _lib.ptr(_f32c(images, "images")),
-                                        _lib.ptr(_f32c(masks, "masks")), _lib.ptr(_f32c(w2cs, "w2cs")),
-                                        _lib.ptr(_f32c(Ks, "Ks")), B, F, N, Fs, 1 if render_depth else 0,
-                                        _lib.ptr(pix), _lib.ptr(mk), _lib.ptr(dep), _lib.stream_ptr()),
-                   "g3c_render_cache")
+        pts, w2cs, Ks = _f32c(points, "points"), _f32c(w2cs, "w2cs"), _f32c(Ks, "Ks")
+        _lib.check(lib.g3c_render_cache(ws, _lib.ptr(pts), _lib.ptr(_f32c(images, "images")),
+                                        _lib.ptr(_f32c(masks, "masks")), _lib.ptr(w2cs), _lib.ptr(Ks), B, F, N, Fs,
+                                        1 if dep is not None else 0, _lib.ptr(pix), _lib.ptr(mk), _lib.ptr(dep),
+                                        _lib.stream_ptr()), "g3c_render_cache")
+        if fg:
+            assert boundary_masks.shape == (B, Fs, N, H, W)
+            bm = boundary_masks.to(device=dev, dtype=torch.uint8).contiguous()
+            _lib.check(lib.g3c_render_cache_occlusion(_lib.ptr(pts), _lib.ptr(bm), _lib.ptr(w2cs), _lib.ptr(Ks), B, F, N,
+                                                      Fs, _lib.ptr(pix), _lib.ptr(mk), _lib.ptr(dep), H, W,
+                                                      _lib.stream_ptr()), "g3c_render_cache_occlusion")
     return (dep if render_depth else pix), mk

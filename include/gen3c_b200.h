@@ -83,7 +83,18 @@ int g3c_unproject_points(const float* depth, const float* w2c, const float* K, c
 int g3c_reliable_depth_mask(const float* depth, int b, int H, int W, int window, float ratio_thresh,
                             float eps, uint8_t* out, void* stream);
 
-/* EXPERIMENTAL (not yet validated on hardware): the foreground-masking occlusion pass of
+/* Second stage of align_depth(..., alignment_method="non_rigid") as called by Cache3D_Buffer.update_cache (reference:
+ * cosmos_predict1/diffusion/inference/camera_utils.py:292-345, cache_3d.py:262-282): a per-pixel scale map fitted with
+ * `num_iters` Adam steps (lr, betas .9/.999, eps 1e-8) to
+ *     mean |unproject(depth*sc) - unproject(target_depth)| over target_mask  +  lambda_arap * mean |box3(sc) - sc| ,
+ * gradient in closed form, one stencil kernel per iteration.  `depth` is the source depth AFTER the rigid (affine
+ * inverse-depth) stage; `c2w` is the matrix the reference hands to unproject_points (which inverts it).
+ *   depth, target_depth [H,W] f32, target_mask [H,W] u8, K [9], c2w [16] (device)  ->  out_depth [H,W] = depth * sc */
+int g3c_align_depth_nonrigid(const float* depth, const float* target_depth, const uint8_t* target_mask, const float* K,
+                             const float* c2w, int H, int W, int num_iters, float lambda_arap, float lr,
+                             float* out_depth, void* stream);
+
+/* The foreground-masking occlusion pass of
  * forward_warp(foreground_masking=True, boundary_mask=...) — reference forward_warp_utils_pytorch.py:285-335 with
  * points_to_mesh :49-132, get_camera_rays :151-168 and the NVIDIA-Warp kernel ray_triangle_intersection_warp.py:23-105.
  * Post-processes the outputs of g3c_forward_warp(..., G3C_WARP_RENDER_DEPTH): pixels whose 1/4-resolution boundary mesh
@@ -92,6 +103,13 @@ int g3c_reliable_depth_mask(const float* depth, int b, int H, int W, int window,
  *   mask [b,1,H,W], depth [b,H,W]. */
 int g3c_foreground_occlusion(const float* points, const unsigned char* boundary, const float* w2c, const float* K, int b,
                              int C, int H, int W, float* warped, float* mask, float* depth, void* stream);
+
+/* The same pass over the items of a cache render (Cache3D_Base.render_cache with foreground_masking=True, reference
+ * cache_3d.py:168-215): items (B F N) as in g3c_render_cache, each with its source frame's points / boundary mask and its
+ * target camera.  In/out: the pixels / masks / depth that g3c_render_cache(render_depth=1) wrote. */
+int g3c_render_cache_occlusion(const float* points, const unsigned char* boundary, const float* w2cs, const float* Ks, int B,
+                               int F_target, int N, int src_frames, float* pixels, float* masks, float* depth, int H, int W,
+                               void* stream);
 
 /* ===================================== Path D: DiT denoise step =============================== */
 
@@ -184,6 +202,17 @@ int g3c_dit_cp_import(g3c_dit_t* h, const void* handles, int n);
 int g3c_dit_cp_mode(const g3c_dit_t* h); /* 0 = off, 1 = peer-memory (fused), 2 = NCCL */
 int g3c_dit_disable_cp(g3c_dit_t* h);
 
+/* Classifier-free-guidance parallelism (an extension; SURVEY.md §8e "CFG x CP hybrid"): the two forwards of a denoise
+ * step (model_v2w.py:141-142) run on two ranks that hold the SAME latent slice — role 0 evaluates the conditional
+ * branch, role 1 the unconditional one — and g3c_denoise_step exchanges the two network outputs through peer memory
+ * (one copy-engine push of 16*T*H*W bf16 per rank and step, a system-scope flag, a one-warp wait kernel) before both
+ * ranks apply the identical sampler update.  Composes with context parallelism (cfg 2 x cp N/2).  role < 0 disables.
+ * After g3c_dit_set_shape: g3c_dit_cfg_export (64-byte IPC handle of this rank's exchange region) and
+ * g3c_dit_cfg_import (the partner's handle). */
+int g3c_dit_enable_cfg_parallel(g3c_dit_t* h, int role);
+int g3c_dit_cfg_export(g3c_dit_t* h, void* out_handle64);
+int g3c_dit_cfg_import(g3c_dit_t* h, const void* partner_handle64);
+
 /* Fix the token grid: T_local latent frames on this rank (of T_local*cp_size), latent H x W,
  * context length, fps.  Allocates the workspace and precomputes the abs-pos / RoPE tables. */
 int g3c_dit_set_shape(g3c_dit_t* h, int T_local, int H_latent, int W_latent, int ctx_len, float fps);
@@ -208,6 +237,10 @@ typedef struct g3c_step_args {
   const void* ctx_uncond;
   float sigma, sigma_next, sigma_data, sigma_aug, guidance;
   void* xt_next;         /* bf16 [16,T,H,W] */
+  const void* cond_mask_uncond; /* bf16 [1,T,H,W] uncondition.condition_video_input_mask (all zeros with
+                                   add_input_frames_guidance, model_v2w.py:76-80) or NULL = same as cond_mask */
+  void* net_output;      /* optional out, bf16 [16,T,H,W]: net_output_cond + guidance * (cond - uncond)
+                            (model_v2w.py:143) before the indicator replacement; NULL = not stored */
 } g3c_step_args;
 
 /* One loop body of DiffusionV2WModel.generate_samples_from_batch (reference:
@@ -219,6 +252,10 @@ int g3c_denoise_step(g3c_dit_t* h, const g3c_step_args* a, void* stream);
  * of g3c_dit_forward is bracketed by CUDA events on the launching stream.  Categories:
  * 0 GEMM, 1 self-attention, 2 cross-attention, 3 elementwise, 4 comm, 5 B=1 vector ops.
  * g3c_dit_profile_read synchronises, sums elapsed ms / launch counts per category and resets. */
+/* g3c_dit_profile_wait_ms: mean time per CTA and launch (ms, summed over the launches since the last read) that the
+ * attention kernel's TMA warps spent polling a peer's K/V arrival flag under context parallelism — an upper bound of the
+ * exposed exchange (the ring may still hold tiles for the MMA warp while the loader waits). */
+int g3c_dit_profile_wait_ms(g3c_dit_t* h, float* ms);
 #define G3C_PROFILE_CATEGORIES 6
 int g3c_dit_profile(g3c_dit_t* h, int enable);
 int g3c_dit_profile_read(g3c_dit_t* h, float* ms_by_category, int* launches_by_category, int ncat);

@@ -115,6 +115,11 @@ TINY = DitCfg(model_channels=256, num_blocks=2, num_heads=2, ffn_dim=1024, conte
 TINY_SHAPE = dict(T=2, H=16, W=16, ctx_len=128)  # L = 2*8*8 = 128 tokens
 
 
+# one block at the full BASELINE width on two latent frames of the 720p grid: 2 * 44 * 80 = 7 040 tokens (55 x 128)
+FULLWIDTH_1BLOCK = DitCfg(num_blocks=1)
+FULLWIDTH_SHAPE = dict(T=2, H=88, W=160, ctx_len=512)
+
+
 def dit_inputs(cfg: DitCfg, T: int, H: int, W: int, ctx_len: int, seed: int = 1, x_scale: float = 1.0):
     """bf16-representable fp32 tensors: x, cond_mask, cond_pose, padding_mask, ctx (cond/uncond), timestep."""
     g = torch.Generator().manual_seed(seed)

@@ -102,13 +102,33 @@ def random_state_dict(cfg: DitCfg, seed: int = 0, std: float = 0.02, dtype=torch
     return sd
 
 
+def random_state_dict_on(cfg: DitCfg, device, seed: int = 0, std: float = 0.02, dtype=torch.float32):
+    """Same distribution as `random_state_dict`, drawn with the generator of `device` (a 7B-parameter set takes
+    seconds on the GPU instead of minutes on the host).  Values are bf16-representable; the numbers differ from the
+    CPU generator's, so fixtures minted on the CPU must keep using `random_state_dict`."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    sd = {}
+    for k, shp in state_dict_shapes(cfg).items():
+        if k == "pos_embedder.seq":
+            sd[k] = torch.arange(shp[0], dtype=torch.float32, device=device)
+            continue
+        if k.endswith(".1.weight") and len(shp) == 1 or k == "affline_norm.weight":
+            t = 1.0 + 0.1 * torch.randn(shp, generator=g, device=device)
+        else:
+            t = std * torch.randn(shp, generator=g, device=device)
+            if "adaLN_modulation.2" in k or "linear_2" in k:
+                t = t * 2.0
+        sd[k] = t.to(torch.bfloat16).to(dtype)
+    return sd
+
+
 # --------------------------------------------------------------------------------------------------
 # building blocks
 # --------------------------------------------------------------------------------------------------
 def timestep_sinusoid(t: torch.Tensor, D: int) -> torch.Tensor:
     """blocks.py:38-51: [cos(t*e) | sin(t*e)], e_i = exp(-ln(1e4) * i / half)."""
     half = D // 2
-    e = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half)
+    e = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     a = t.float()[:, None] * e[None]
     return torch.cat([torch.cos(a), torch.sin(a)], dim=-1)
 
@@ -118,7 +138,7 @@ def rms_norm(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-6) -> torch.Tenso
     return xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps) * w.float()
 
 
-def rope_angles(cfg: DitCfg, T: int, Hp: int, Wp: int, fps: float, t0: int = 0) -> torch.Tensor:
+def rope_angles(cfg: DitCfg, T: int, Hp: int, Wp: int, fps: float, t0: int = 0, device=None) -> torch.Tensor:
     """position_embedding.py:106-187 -> [T*Hp*Wp, 128] fp32 angles (t | h | w) repeated twice."""
     dim = 128
     dim_h = dim // 6 * 2
@@ -170,6 +190,17 @@ def attention(q, k, v, heads: int) -> torch.Tensor:
     qh = q.reshape(Lq, heads, 128).permute(1, 0, 2)
     kh = k.reshape(-1, heads, 128).permute(1, 0, 2)
     vh = v.reshape(-1, heads, 128).permute(1, 0, 2)
+    if q.is_cuda and q.dtype == torch.float32:
+        # fp32 on the GPU: explicit matmul / softmax in query chunks (plain fp32 FMA GEMMs; torch's fused fp32 SDPA
+        # kernels may use TF32-class tensor instructions, which an oracle must not)
+        Lk = kh.shape[1]
+        rows = max(128, min(Lq, (1 << 31) // max(1, heads * Lk)))  # <= 8 GiB of fp32 scores per chunk
+        out = torch.empty(heads, Lq, 128, dtype=q.dtype, device=q.device)
+        for r0 in range(0, Lq, rows):
+            sc = torch.matmul(qh[:, r0:r0 + rows], kh.transpose(1, 2)) * (128 ** -0.5)
+            out[:, r0:r0 + rows] = torch.matmul(torch.softmax(sc, dim=-1), vh)
+            del sc
+        return out.permute(1, 0, 2).reshape(Lq, D)
     o = F.scaled_dot_product_attention(qh[None], kh[None], vh[None])[0]
     return o.permute(1, 0, 2).reshape(Lq, D)
 
@@ -187,85 +218,107 @@ def unpatchify(y: torch.Tensor, T: int, Hp: int, Wp: int, C: int) -> torch.Tenso
     return y.reshape(C, T, Hp * 2, Wp * 2)
 
 
-def modulation_vectors(sd, cfg: DitCfg, timestep: float):
+def modulation_vectors(sd, cfg: DitCfg, timestep: float, dt=torch.float32):
     D = cfg.model_channels
-    s = timestep_sinusoid(torch.tensor([timestep], dtype=torch.float32), D)[0]
-    h1 = sd["t_embedder.1.linear_1.weight"].float() @ s
-    lora = sd["t_embedder.1.linear_2.weight"].float() @ F.silu(h1)
-    emb = rms_norm(s, sd["affline_norm.weight"])
+    w1 = sd["t_embedder.1.linear_1.weight"]
+    s = timestep_sinusoid(torch.tensor([timestep], dtype=torch.float32, device=w1.device), D)[0].to(dt)
+    h1 = w1.to(dt) @ s
+    lora = sd["t_embedder.1.linear_2.weight"].to(dt) @ F.silu(h1)
+    emb = rms_norm(s, sd["affline_norm.weight"]).to(dt)
     return s, emb, lora
 
 
 def forward(sd, cfg: DitCfg, x, cond_mask, cond_pose, padding_mask, timestep: float, ctx, fps: float = 24.0,
-            t0: int = 0, T_total: int | None = None, kv_gather=None, return_intermediates: bool = False):
+            t0: int = 0, T_total: int | None = None, kv_gather=None, return_intermediates: bool = False,
+            compute_dtype: torch.dtype = torch.float32, num_blocks: int | None = None):
     """One network forward for B=1.  x [16,T,H,W], cond_mask [1,T,H,W], cond_pose [64,T,H,W] or None
-    (zeros), padding_mask [H,W] or None (zeros), ctx [M, context_dim].  Everything fp32.
+    (zeros), padding_mask [H,W] or None (zeros), ctx [M, context_dim].
+    Runs on the device of `x` (weights in `sd` must live there too) in `compute_dtype`: float32 (the oracle proper;
+    on CUDA the caller switches TF32 off) or bfloat16 (every tensor stored in bf16 between ops as in the
+    reference's bf16 inference run; norms / softmax accumulate in fp32 inside the op, as torch / TE do).
     t0 / kv_gather emulate a context-parallel rank: positions start at latent frame t0 and
-    kv_gather(k, v) returns the K/V of all ranks."""
-    f32 = torch.float32
+    kv_gather(k, v) returns the K/V of all ranks.  num_blocks < cfg.num_blocks stops after that many blocks
+    (error-growth-by-depth measurements) and still applies the final layer."""
+    dt, dev = compute_dtype, x.device
     D, heads = cfg.model_channels, cfg.num_heads
     _, T, H, W = x.shape
     Hp, Wp = H // 2, W // 2
     L = T * Hp * Wp
     npose = cfg.in_channels - 17
-    parts = [x.to(f32), cond_mask.to(f32)]
+    nb = cfg.num_blocks if num_blocks is None else num_blocks
+
+    def w(k):
+        return sd[k].to(device=dev, dtype=dt)
+
+    parts = [x.to(dt), cond_mask.to(dt)]
     if npose > 0:
-        parts.append(cond_pose.to(f32) if cond_pose is not None else torch.zeros(npose, T, H, W))
+        parts.append(cond_pose.to(dt) if cond_pose is not None else torch.zeros(npose, T, H, W, dtype=dt, device=dev))
     if cfg.concat_padding_mask:
-        pm = padding_mask.to(f32) if padding_mask is not None else torch.zeros(H, W)
+        pm = padding_mask.to(dt) if padding_mask is not None else torch.zeros(H, W, dtype=dt, device=dev)
         parts.append(pm[None, None].expand(1, T, H, W))
     tok = patchify(torch.cat(parts, 0))
-    h = tok @ sd["x_embedder.proj.1.weight"].float().T  # [L, D]
-    pos = abs_pos_emb(sd, cfg, T, Hp, Wp, t0)
-    ang = rope_angles(cfg, T, Hp, Wp, fps, t0)
-    s, emb, lora = modulation_vectors(sd, cfg, timestep)
+    h = tok @ w("x_embedder.proj.1.weight").T  # [L, D]
+    sdv = sd if sd["extra_pos_embedder.pos_emb_t"].device == dev else {k: sd[k].to(dev) for k in (
+        "extra_pos_embedder.pos_emb_t", "extra_pos_embedder.pos_emb_h", "extra_pos_embedder.pos_emb_w")}
+    pos = abs_pos_emb(sdv, cfg, T, Hp, Wp, t0).to(dt)
+    ang = rope_angles(cfg, T, Hp, Wp, fps, t0, device=dev)
+    s, emb, lora = modulation_vectors(sd, cfg, timestep, dt)
     inter = {}
 
     def mod(prefix, n):
-        a = sd[prefix + "adaLN_modulation.1.weight"].float() @ F.silu(emb)
-        m = sd[prefix + "adaLN_modulation.2.weight"].float() @ a + lora[: n * D]
+        a = w(prefix + "adaLN_modulation.1.weight") @ F.silu(emb)
+        m = w(prefix + "adaLN_modulation.2.weight") @ a + lora[: n * D]
         return m.chunk(n)
 
     def ln(v):
         return F.layer_norm(v, (D,), eps=1e-6)
 
-    ctx = ctx.to(f32)
-    for i in range(cfg.num_blocks):
+    def nrm(v, key):  # TE RMSNorm: fp32 inside, stored in the compute dtype
+        return rms_norm(v, sd[key].to(dev)).to(dt)
+
+    def rope(v):
+        return apply_rope(v.float(), ang).to(dt)
+
+    ctx = ctx.to(dt)
+    for i in range(nb):
         h = h + pos
         # FA
         p = f"blocks.block{i}.blocks.0."
         shift, scale, gate = mod(p, 3)
         xn = ln(h) * (1 + scale) + shift
-        q = xn @ sd[p + "block.attn.to_q.0.weight"].float().T
-        k = xn @ sd[p + "block.attn.to_k.0.weight"].float().T
-        v = xn @ sd[p + "block.attn.to_v.0.weight"].float().T
-        q = apply_rope(rms_norm(q.reshape(L, heads, 128), sd[p + "block.attn.to_q.1.weight"]), ang).reshape(L, D)
-        k = apply_rope(rms_norm(k.reshape(L, heads, 128), sd[p + "block.attn.to_k.1.weight"]), ang).reshape(L, D)
+        q = xn @ w(p + "block.attn.to_q.0.weight").T
+        k = xn @ w(p + "block.attn.to_k.0.weight").T
+        v = xn @ w(p + "block.attn.to_v.0.weight").T
+        q = rope(nrm(q.reshape(L, heads, 128), p + "block.attn.to_q.1.weight")).reshape(L, D)
+        k = rope(nrm(k.reshape(L, heads, 128), p + "block.attn.to_k.1.weight")).reshape(L, D)
         if kv_gather is not None:
             k, v = kv_gather(i, k, v)
         o = attention(q, k, v, heads)
-        h = h + gate * (o @ sd[p + "block.attn.to_out.0.weight"].float().T)
+        h = h + gate * (o @ w(p + "block.attn.to_out.0.weight").T)
+        del q, k, v, o
         if return_intermediates and i == 0:
-            inter["fa0_q"], inter["fa0_k"], inter["fa0_attn"], inter["fa0_x"] = q, k, o, h.clone()
+            inter["fa0_x"] = h.clone()
         # CA
         p = f"blocks.block{i}.blocks.1."
         shift, scale, gate = mod(p, 3)
         xn = ln(h) * (1 + scale) + shift
-        q = xn @ sd[p + "block.attn.to_q.0.weight"].float().T
-        kc = ctx @ sd[p + "block.attn.to_k.0.weight"].float().T
-        vc = ctx @ sd[p + "block.attn.to_v.0.weight"].float().T
-        q = rms_norm(q.reshape(L, heads, 128), sd[p + "block.attn.to_q.1.weight"]).reshape(L, D)
-        kc = rms_norm(kc.reshape(-1, heads, 128), sd[p + "block.attn.to_k.1.weight"]).reshape(-1, D)
+        q = xn @ w(p + "block.attn.to_q.0.weight").T
+        kc = ctx @ w(p + "block.attn.to_k.0.weight").T
+        vc = ctx @ w(p + "block.attn.to_v.0.weight").T
+        q = nrm(q.reshape(L, heads, 128), p + "block.attn.to_q.1.weight").reshape(L, D)
+        kc = nrm(kc.reshape(-1, heads, 128), p + "block.attn.to_k.1.weight").reshape(-1, D)
         o = attention(q, kc, vc, heads)
-        h = h + gate * (o @ sd[p + "block.attn.to_out.0.weight"].float().T)
+        h = h + gate * (o @ w(p + "block.attn.to_out.0.weight").T)
+        del q, o
         # MLP
         p = f"blocks.block{i}.blocks.2."
         shift, scale, gate = mod(p, 3)
         xn = ln(h) * (1 + scale) + shift
-        hid = F.gelu(xn @ sd[p + "block.layer1.weight"].float().T)
-        h = h + gate * (hid @ sd[p + "block.layer2.weight"].float().T)
+        hid = F.gelu(xn @ w(p + "block.layer1.weight").T)
+        h = h + gate * (hid @ w(p + "block.layer2.weight").T)
+        del hid, xn
     shift, scale = mod("final_layer.", 2)
-    y = (ln(h) * (1 + scale) + shift) @ sd["final_layer.linear.weight"].float().T
+    y = (ln(h) * (1 + scale) + shift) @ w("final_layer.linear.weight").T
     out = unpatchify(y, T, Hp, Wp, cfg.out_channels)
     if return_intermediates:
         return out, inter
@@ -292,7 +345,7 @@ def bf16(t: torch.Tensor) -> torch.Tensor:
 
 
 def denoise_step(net, xt, gt, noise, indicator_t, sigma: float, sigma_next: float, guidance: float,
-                 sigma_data: float = 0.5, sigma_aug: float = 0.001):
+                 sigma_data: float = 0.5, sigma_aug: float = 0.001, return_net_output: bool = False):
     """model_v2w.py:130-149 for one step.  net(x_in, timestep, cond: bool) -> [16,T,H,W] (fp32).
     xt, gt [16,T,H,W]; noise fp32; indicator_t [T].  bf16 storage of x~, x_in, net outputs, x_next as in
     the reference's bf16 tensors; everything else fp32."""
@@ -307,10 +360,12 @@ def denoise_step(net, xt, gt, noise, indicator_t, sigma: float, sigma_next: floa
     oc = bf16(net(x_in, t, True))
     ou = bf16(net(x_in, t, False))
     o = oc + guidance * (oc - ou)
+    net_output = o
     c_skip = sigma_data ** 2 / (sigma ** 2 + sigma_data ** 2)
     c_out = sigma * sigma_data / math.sqrt(sigma ** 2 + sigma_data ** 2)
     lat = (gt.float() - c_skip * xs) / c_out
     o = ind * lat + (1 - ind) * o
     x0 = c_skip * xs + c_out * o
     d = (xs - x0) / sigma
-    return bf16(xs + d * (sigma_next - sigma))
+    nxt = bf16(xs + d * (sigma_next - sigma))
+    return (nxt, net_output) if return_net_output else nxt

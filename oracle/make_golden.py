@@ -201,10 +201,163 @@ def mint_dit():
     return 0
 
 
+def mint_cache_classes():
+    """The reference's own Cache3D_Buffer / Cache3D_BufferSelector / Cache4D objects (cache_3d.py:26-433) and align_depth
+    (camera_utils.py:225-347) executed on CPU -> tests/golden/warp_cache_classes.npz: ring of 2 with
+    update_cache(depth_alignment=False), the rigid and non-rigid depth alignment of update_cache (default arguments),
+    top-K buffer selection, per-frame 4D cache, unproject_points(is_depth=False) and forward_warp(depth1=...)."""
+    ref = ref_stubs.reference_warp_module()
+    cm = ref_stubs.reference_cache_module()
+    import cosmos_predict1.diffusion.inference.camera_utils as cu
+
+    out = {}
+    c3, c6 = cases.warp_case("R3"), cases.warp_case("R6")
+    h, w = 96, 128
+    K = t(c3["K"][:1])
+    F = 2
+    w2cs = t(cases.pan_trajectory(F, 0.08))[None]
+    Ks = K[None].expand(1, F, 3, 3).contiguous()
+    # ---- Cache3D_Buffer: ring of 2, three inserts (append, then overwrite slot 0 twice), no alignment
+    cache = cm.Cache3D_Buffer(frame_buffer_max=2, noise_aug_strength=0, generator=None,
+                              input_image=t(c3["image"][:1]), input_depth=t(c3["depth"][:1]), input_w2c=t(c3["w2c_src"][:1]),
+                              input_intrinsics=K, device="cpu", filter_points_threshold=0.05, foreground_masking=False)
+    with torch.no_grad():
+        p0, m0 = cache.render_cache(w2cs, Ks)
+        new_w2c = t(cases.look(0.02, -0.01, (0.03, 0.0, 0.01)))[None]
+        cache.update_cache(t(c3["image"][1:2]), t(c3["depth"][1:2]), new_w2c, new_intrinsics=K, depth_alignment=False)
+        p1, m1 = cache.render_cache(w2cs, Ks)
+        new_w2c2 = t(cases.look(-0.03, 0.005, (-0.02, 0.01, 0.0)))[None]
+        cache.update_cache(t(c6["image"]), t(c6["depth"]), new_w2c2, new_intrinsics=K, depth_alignment=False)
+        p2, m2 = cache.render_cache(w2cs, Ks)
+        d2, dm2 = cache.render_cache(w2cs, Ks, render_depth=True)
+    out.update(buf_p0=p0.numpy(), buf_m0=m0.numpy(), buf_p1=p1.numpy(), buf_m1=m1.numpy(), buf_p2=p2.numpy(),
+               buf_m2=m2.numpy(), buf_d2=d2.numpy(), buf_new_w2c=new_w2c.numpy(), buf_new_w2c2=new_w2c2.numpy())
+    # ---- update_cache with depth alignment (the default path): rigid and non-rigid (100 Adam steps)
+    for method in ("rigid", "non_rigid"):
+        cache = cm.Cache3D_Buffer(frame_buffer_max=2, noise_aug_strength=0, generator=None,
+                                  input_image=t(c3["image"][:1]), input_depth=t(c3["depth"][:1]), input_w2c=t(c3["w2c_src"][:1]),
+                                  input_intrinsics=K, device="cpu", filter_points_threshold=0.05, foreground_masking=False)
+        # a new depth map that disagrees with the cache by an affine map of inverse depth plus a smooth non-rigid part
+        nd = c3["depth"][:1] * (1.15 + 0.05 * cases.smooth_depth(h, w)[None, None] / 3.5) + 0.2
+        cache.update_cache(t(c3["image"][1:2]), t(nd.astype(np.float32)), new_w2c, new_intrinsics=K, depth_alignment=True,
+                           alignment_method=method)
+        with torch.no_grad():
+            pa, ma = cache.render_cache(w2cs, Ks)
+        out[f"align_{method}_points"] = cache.input_points[:, :, 0, 0].numpy()
+        out[f"align_{method}_pixels"] = pa.numpy()
+        out[f"align_{method}_masks"] = ma.numpy()
+    out["align_new_depth"] = nd.astype(np.float32)
+    # the aligned depth itself, from align_depth called the way update_cache calls it
+    cache = cm.Cache3D_Buffer(frame_buffer_max=2, noise_aug_strength=0, generator=None,
+                              input_image=t(c3["image"][:1]), input_depth=t(c3["depth"][:1]), input_w2c=t(c3["w2c_src"][:1]),
+                              input_intrinsics=K, device="cpu", filter_points_threshold=0.05, foreground_masking=False)
+    with torch.no_grad():
+        td, tm = cache.render_cache(new_w2c.unsqueeze(1), K.unsqueeze(1), render_depth=True)
+    td, tm = td[:, :, 0], tm[:, :, 0]
+    rigid = cu.align_depth(t(nd.astype(np.float32)).squeeze(), td.squeeze(), tm.bool().squeeze())
+    with torch.enable_grad():
+        nonrigid = cu.align_depth(t(nd.astype(np.float32)).squeeze(), td.squeeze(), tm.bool().squeeze(), k=K.squeeze(),
+                                  c2w=torch.inverse(new_w2c.squeeze()), alignment_method="non_rigid", num_iters=100,
+                                  lambda_arap=0.1, smoothing_kernel_size=3).detach()
+    out.update(align_target_depth=td.numpy(), align_target_mask=tm.numpy(), align_rigid_depth=rigid.numpy(),
+               align_nonrigid_depth=nonrigid.numpy())
+    # ---- Cache3D_BufferSelector: 3 buffers at init, keep the 2 with the largest overlap, near-full masking
+    imgs = np.stack([c3["image"][0], c3["image"][1], c6["image"][0]])[None]          # B N C H W
+    deps = np.stack([c3["depth"][0], c3["depth"][1], c6["depth"][0]])[None]
+    srcs = np.stack([np.eye(4, dtype=np.float32), cases.look(0.3, 0.0, (0.6, 0.0, 0.0)), cases.look(-0.02, 0.0, (0.01, 0, 0))])[None]
+    sel = cm.Cache3D_BufferSelector(frame_buffer_max=2, input_image=t(imgs), input_depth=t(deps), input_w2c=t(srcs),
+                                    input_intrinsics=K[None].expand(1, 3, 3, 3).contiguous(),
+                                    input_format=["B", "N", "C", "H", "W"], device="cpu", filter_points_threshold=0.05)
+    with torch.no_grad():
+        ps, ms = sel.render_cache(w2cs, Ks)
+    out.update(sel_images=imgs, sel_depths=deps, sel_w2c=srcs, sel_pixels=ps.numpy(), sel_masks=ms.numpy())
+    # ---- Cache4D: one cache frame per target frame, start_frame_idx = 1
+    imgs4 = np.stack([c3["image"][0], c3["image"][1], c6["image"][0]])[None]         # B F C H W
+    c4 = cm.Cache4D(input_image=t(imgs4), input_depth=t(deps), input_w2c=t(srcs),
+                    input_intrinsics=K[None].expand(1, 3, 3, 3).contiguous(), input_format=["B", "F", "C", "H", "W"],
+                    device="cpu", filter_points_threshold=0.05)
+    with torch.no_grad():
+        p4, m4 = c4.render_cache(w2cs, Ks, start_frame_idx=1)
+    out.update(c4_pixels=p4.numpy(), c4_masks=m4.numpy())
+    # ---- unproject_points(is_depth=False) and forward_warp with depth1 given (is_depth True / False)
+    with torch.no_grad():
+        pr = ref.unproject_points(t(c6["depth"]), t(c6["w2c_src"]), t(c6["K"]), is_depth=False)
+        fw = ref.forward_warp(t(c6["image"]), None, t(c6["depth"]), t(c6["w2c_src"]), t(c6["w2c_tgt"]), t(c6["K"]), None,
+                              render_depth=True)
+        fr = ref.forward_warp(t(c6["image"]), None, t(c6["depth"]), t(c6["w2c_src"]), t(c6["w2c_tgt"]), t(c6["K"]), None,
+                              is_depth=False)
+    out.update(ray_points=pr.numpy(), d1_warped=fw[0].numpy(), d1_mask=fw[1].numpy(), d1_depth=fw[2].numpy(),
+               d1_flow=fw[3].numpy(), d1r_warped=fr[0].numpy(), d1r_mask=fr[1].numpy(), d1r_flow=fr[3].numpy())
+    # ---- camera trajectories (camera_utils.py:142-222), 4x4 host arithmetic
+    w0 = t(cases.look(0.05, -0.02, (0.1, 0.0, 0.2)))
+    for ty in ("left", "right", "up", "down", "zoom_in", "zoom_out", "clockwise", "counterclockwise"):
+        for rot in ("center_facing", "no_rotation", "trajectory_aligned"):
+            w2, k2 = cu.generate_camera_trajectory(ty, w0, K[0], 7, 0.3, rot, center_depth=1.7, device="cpu")
+            out[f"traj_{ty}_{rot}"] = w2.numpy()
+    out["traj_w0"] = w0.numpy()
+    np.savez_compressed(os.path.join(OUT, "warp_cache_classes.npz"), **out)
+    # the restated oracle against the same runs
+    po = warp_oracle.unproject_points(c6["depth"], c6["w2c_src"], c6["K"], is_depth=False)
+    print("== Path R classes: ring/selector/4D/alignment goldens written; oracle unproject(is_depth=False) err %.2e; "
+          "non-rigid vs rigid depth change mean %.3e ==" % (float(np.abs(po - pr.numpy()).max()),
+                                                              float((nonrigid - rigid).abs().mean())))
+    return 0
+
+
+def _ref_net(Net, cfg, **over):
+    kw = dict(max_img_h=cfg.max_h * 2, max_img_w=cfg.max_w * 2, max_frames=cfg.max_frames, in_channels=cfg.in_channels,
+              out_channels=cfg.out_channels, patch_spatial=2, patch_temporal=1, model_channels=cfg.model_channels,
+              block_config="FA-CA-MLP", num_blocks=cfg.num_blocks, num_heads=cfg.num_heads, concat_padding_mask=True,
+              pos_emb_cls="rope3d", pos_emb_learnable=False, pos_emb_interpolation="crop", block_x_format="THWBD",
+              affline_emb_norm=True, use_adaln_lora=True, adaln_lora_dim=cfg.adaln_lora_dim,
+              rope_t_extrapolation_ratio=cfg.rope_t_ratio, crossattn_emb_channels=cfg.context_dim)
+    kw.update(over)
+    return Net(**kw)
+
+
+def mint_dit_fullwidth():
+    """ONE block of the network at the full BASELINE width (D=4096, 32 heads, ffn 16 384, ctx 512x1024, position tables
+    240/128) on two latent frames of the 720p grid (7 040 tokens), executed by the reference's own class in fp32 on the
+    CPU -> tests/golden/dit_fullwidth.npz (output only: the weights are regenerated from the seed)."""
+    Net = ref_stubs.reference_dit_class()
+    from cosmos_predict1.diffusion.conditioner import DataType
+
+    cfg, shp = cases.FULLWIDTH_1BLOCK, cases.FULLWIDTH_SHAPE
+    sd = dit_oracle.random_state_dict(cfg, seed=21)
+    net = _ref_net(Net, cfg)
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected and all("_extra_state" in m for m in missing)
+    net.eval()
+    inp = cases.dit_inputs(cfg, **shp, seed=22)
+    T = shp["T"]
+    with torch.no_grad():
+        out = net(x=inp["x"][None], timesteps=torch.tensor([inp["timestep"]]), crossattn_emb=inp["ctx_c"][None],
+                  crossattn_mask=None, fps=torch.tensor([24.0]), image_size=None, padding_mask=inp["padding"][None, None],
+                  data_type=DataType.VIDEO, condition_video_input_mask=inp["cond_mask"][None],
+                  condition_video_indicator=torch.zeros(1, 1, T, 1, 1), condition_video_pose=inp["pose"][None])[0].float()
+    o = dit_oracle.forward(sd, cfg, inp["x"], inp["cond_mask"], inp["pose"], inp["padding"], inp["timestep"], inp["ctx_c"])
+    e = float((o - out).norm() / out.norm())
+    ob = dit_oracle.forward({k: v.to(torch.bfloat16) for k, v in sd.items()}, cfg, inp["x"], inp["cond_mask"], inp["pose"],
+                            inp["padding"], inp["timestep"], inp["ctx_c"], compute_dtype=torch.bfloat16).float()
+    eb = float((ob - out).norm() / out.norm())
+    np.savez_compressed(os.path.join(OUT, "dit_fullwidth.npz"), out_cond=out.numpy(), oracle_bf16_rel_l2=np.float32(eb))
+    print("== Path D (1 block at full width D=4096/32 heads/ffn 16384/ctx 512x1024, 7 040 tokens): restated oracle vs the "
+          "reference's fp32 forward rel-L2 %.2e ; bf16 run of the oracle vs it %.2e ==" % (e, eb))
+    return 0 if e < 1e-4 else 1
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    rc = mint_warp()
-    rc |= mint_dit()
+    only = sys.argv[1:]
+    rc = 0
+    if not only or "warp" in only:
+        rc |= mint_warp()
+    if not only or "classes" in only:
+        rc |= mint_cache_classes()
+    if not only or "dit" in only:
+        rc |= mint_dit()
+    if not only or "fullwidth" in only:
+        rc |= mint_dit_fullwidth()
     sys.exit(rc)
 
 

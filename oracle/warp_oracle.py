@@ -317,3 +317,79 @@ def render_cache(points, images, masks, w2cs, Ks, render_depth=False, chunk=2):
     if render_depth:
         return np.concatenate(douts, 0).reshape(B, F, N, H, W), mk
     return pix, mk
+
+
+# --------------------------------------------------------------------------------------------------
+# depth alignment of Cache3D_Buffer.update_cache
+# --------------------------------------------------------------------------------------------------
+def _quantile(x: np.ndarray, q) -> np.ndarray:
+    """torch.quantile(x, q) with the default linear interpolation, float32."""
+    return np.quantile(x.astype(F32), np.asarray(q, dtype=F32), method="linear").astype(F32)
+
+
+def align_inv_depth_to_depth(source_inv_depth, target_depth, target_mask=None):
+    """camera_utils.py:225-270 — affine fit (scale, bias) of the source inverse depth to the target inverse depth on the
+    10 %..90 % quantile core of both, solved by least squares; returns the aligned DEPTH (h, w)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        target_inv = (F32(1.0) / target_depth.astype(F32)).astype(F32)
+    src_mask = source_inv_depth > 0
+    tdm = target_depth > 0
+    tmask = tdm if target_mask is None else np.logical_and(target_mask > 0, tdm)
+    s_lo, s_hi = _quantile(source_inv_depth[src_mask], [0.1, 0.9])
+    t_lo, t_hi = _quantile(target_inv[tmask], [0.1, 0.9])
+    src_mask = (source_inv_depth > s_lo) & (source_inv_depth < s_hi)
+    tmask = (target_inv > t_lo) & (target_inv < t_hi)
+    m = src_mask & tmask
+    a = np.stack([source_inv_depth[m].astype(np.float64), np.ones(int(m.sum()))], axis=1)
+    sol = np.linalg.lstsq(a, target_inv[m].astype(np.float64), rcond=None)[0]
+    scale, bias = F32(sol[0]), F32(sol[1])
+    with np.errstate(divide="ignore"):
+        return (F32(1.0) / (source_inv_depth.astype(F32) * scale + bias)).astype(F32)
+
+
+def align_depth(source_depth, target_depth, target_mask, k=None, c2w=None, alignment_method="rigid", num_iters=100,
+                lambda_arap=0.1, smoothing_kernel_size=3, lr=0.001):
+    """camera_utils.py:273-347.  rigid: the affine inverse-depth fit.  non_rigid: a per-pixel scale map, 100 Adam steps
+    (lr 1e-3, betas .9/.999, eps 1e-8) on  mean|unproject(src*sc) - unproject(tgt)| over the masked pixels
+    + lambda * mean|box3(sc) - sc|.  The reference differentiates with autograd; here the gradient is written out:
+      d data / d sc_p = sign(e_p) * d_p * (|v_p|_1) / (3 n),  e_p = d_p sc_p - t_p,  v_p = R K^-1 (x, y, 1)
+      d arap / d sc   = (box3(g) - g) / (H W),                 g = sign(box3(sc) - sc)      (zero padding)
+    (R = rotation of inverse(c2w): the reference passes c2w where unproject_points expects w2c, :298-305,:316-322)."""
+    src = source_depth.astype(F32)
+    with np.errstate(divide="ignore"):
+        depth = align_inv_depth_to_depth((F32(1.0) / src).astype(F32), target_depth.astype(F32), target_mask)
+    if alignment_method == "rigid":
+        return depth
+    assert alignment_method == "non_rigid" and k is not None and c2w is not None and smoothing_kernel_size == 3
+    h, w = depth.shape
+    mask = target_mask.astype(bool)
+    n = int(mask.sum())
+    kinv = inverse_with_conversion(k)
+    rot = inverse_with_conversion(c2w)[:3, :3]
+    ys, xs = np.meshgrid(np.arange(h, dtype=F32), np.arange(w, dtype=F32), indexing="ij")
+    rays = np.stack([xs, ys, np.ones_like(xs)], -1) @ kinv.T        # (h, w, 3)
+    v1 = np.abs(rays @ rot.T).sum(-1).astype(F32)                    # |R r|_1
+    coef = np.where(mask, depth * v1 / F32(3 * max(n, 1)), F32(0)).astype(F32)
+    tgt = target_depth.astype(F32)
+
+    def box3(a):
+        p = np.pad(a, 1)
+        s = np.zeros_like(a)
+        for dy in range(3):
+            for dx in range(3):
+                s = s + p[dy:dy + h, dx:dx + w] * F32(1.0 / 9.0)
+        return s.astype(F32)
+
+    sc = np.ones((h, w), F32)
+    m1 = np.zeros((h, w), F32)
+    m2 = np.zeros((h, w), F32)
+    b1, b2, eps = 0.9, 0.999, 1e-8
+    for it in range(1, num_iters + 1):
+        e = depth * sc - tgt
+        g = np.sign(box3(sc) - sc).astype(F32)
+        grad = coef * np.sign(e) + F32(lambda_arap / (h * w)) * (box3(g) - g)
+        m1 = (b1 * m1 + (1 - b1) * grad).astype(F32)
+        m2 = (b2 * m2 + (1 - b2) * grad * grad).astype(F32)
+        denom = np.sqrt(m2) / F32(np.sqrt(1 - b2 ** it)) + F32(eps)
+        sc = (sc - F32(lr / (1 - b1 ** it)) * m1 / denom).astype(F32)
+    return (depth * sc).astype(F32)

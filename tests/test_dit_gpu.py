@@ -68,34 +68,72 @@ def test_wider_forward_matches_oracle():
     assert rel(got, want) < 5e-3, rel(got, want)
 
 
-def test_denoise_step_matches_oracle():
-    """One loop body (model_v2w.py:130-149): frame-0 replacement, CFG combine, EDM Euler update."""
-    from gen3c_b200 import sampler
-
+def _step_case(step_index: int, guidance: float, uncond_mask_zero: bool = False):
+    """Inputs of one loop body at sigma = karras[step_index] with x_t at that noise level."""
     cfg, shp = cases.TINY, cases.TINY_SHAPE
-    T, H, W, M = shp["T"], shp["H"], shp["W"], shp["ctx_len"]
+    T, H, W = shp["T"], shp["H"], shp["W"]
     sd = dit_oracle.random_state_dict(cfg, seed=0)
-    net = build_net(cfg, sd)
-    inp = cases.dit_inputs(cfg, **shp, x_scale=80.0)
     sig = dit_oracle.karras_sigmas(35)
-    sigma, sigma_next, guidance = float(sig[3]), float(sig[4]), 1.0
+    sigma, sigma_next = float(sig[step_index]), float(sig[step_index + 1])
+    inp = cases.dit_inputs(cfg, **shp, x_scale=math.sqrt(sigma ** 2 + 0.25))
     noise = torch.from_numpy(dit_oracle.arch_invariant_rand((16, T, H, W), 1))
     ind = torch.zeros(T)
     ind[0] = 1.0
+    mask_u = torch.zeros_like(inp["cond_mask"]) if uncond_mask_zero else inp["cond_mask"]
 
-    def onet(x_in, t, cond):
-        return dit_oracle.forward(sd, cfg, x_in, inp["cond_mask"], inp["pose"] if cond else None, inp["padding"], t,
-                                  inp["ctx_c"] if cond else inp["ctx_u"])
+    def onet(x_in, t, cond, swap=False, zero=False):
+        if zero:
+            return torch.zeros_like(x_in)
+        c = cond != swap
+        return dit_oracle.forward(sd, cfg, x_in, inp["cond_mask"] if c else mask_u, inp["pose"] if c else None,
+                                  inp["padding"], t, inp["ctx_c"] if c else inp["ctx_u"])
 
-    want = dit_oracle.denoise_step(onet, inp["x"], inp["gt"], noise, ind, sigma, sigma_next, guidance)
+    return cfg, sd, inp, noise, ind, mask_u, sigma, sigma_next, onet
+
+
+@pytest.mark.parametrize("step_index,uncond_mask_zero", [(20, False), (24, True), (3, False)])
+def test_denoise_step_matches_oracle(step_index, uncond_mask_zero):
+    """One loop body (model_v2w.py:130-149): frame-0 replacement, CFG combine, EDM Euler update — checked on the
+    CFG-combined network output AND on x_{t-1}, with negative controls: at sigma <= 1 the network carries a large
+    share of x_{t-1}, so a zeroed network or swapped cond / uncond branches must miss the network-output tolerance by
+    >= 10x and the x_{t-1} tolerance by >= 5x (at sigma = 46.6, third case, x_{t-1} alone could not tell: there the
+    network-output check carries the test)."""
+    from gen3c_b200 import sampler
+
+    guidance = 1.5
+    cfg, sd, inp, noise, ind, mask_u, sigma, sigma_next, onet = _step_case(step_index, guidance, uncond_mask_zero)
+    want, want_o = dit_oracle.denoise_step(lambda x, t, c: onet(x, t, c), inp["x"], inp["gt"], noise, ind, sigma,
+                                           sigma_next, guidance, return_net_output=True)
+    net = build_net(cfg, sd)
     bf = torch.bfloat16
+    net_out = torch.empty(inp["x"].shape, device="cuda", dtype=bf)
     got = sampler.denoise_step(net, inp["x"].cuda().to(bf), inp["gt"].cuda().to(bf), noise.cuda(), ind.cuda(),
                                inp["cond_mask"].cuda().to(bf), inp["pose"].cuda().to(bf),
                                inp["padding"].cuda().to(bf), inp["ctx_c"].cuda().to(bf), inp["ctx_u"].cuda().to(bf),
-                               sigma, sigma_next, guidance).float().cpu()
-    assert rel(got, want) < 5e-3, rel(got, want)
+                               sigma, sigma_next, guidance,
+                               cond_mask_uncond=mask_u.cuda().to(bf) if uncond_mask_zero else None,
+                               net_output=net_out).float().cpu()
+    tol, tol_x = 5e-3, 1e-3   # network output: bf16 engine vs fp32 oracle; x_{t-1}: north_star's 1e-3
+    e_out, e_x = rel(net_out.float().cpu(), want_o), rel(got, want)
+    print(f"sigma {sigma:.3f}: net_output rel-L2 {e_out:.2e}, x_next rel-L2 {e_x:.2e}")
+    assert e_out < tol, e_out
+    assert e_x < tol_x, e_x
     # frame 0 is driven by gt_latent, not by the network (indicator = 1)
-    assert rel(got[:, 0], want[:, 0]) < 5e-3
+    assert rel(got[:, 0], want[:, 0]) < tol_x
+    # ---- negative controls (oracle only): the assertions above can fail
+    bad_swap, bad_swap_o = dit_oracle.denoise_step(lambda x, t, c: onet(x, t, c, swap=True), inp["x"], inp["gt"], noise, ind,
+                                                   sigma, sigma_next, guidance, return_net_output=True)
+    bad_zero, bad_zero_o = dit_oracle.denoise_step(lambda x, t, c: onet(x, t, c, zero=True), inp["x"], inp["gt"], noise, ind,
+                                                   sigma, sigma_next, guidance, return_net_output=True)
+    assert rel(bad_swap_o, want_o) > 10 * tol and rel(bad_zero_o, want_o) > 10 * tol
+    if sigma <= 1.0:
+        assert rel(bad_swap, want) > 5 * tol_x and rel(bad_zero, want) > 5 * tol_x
+    if uncond_mask_zero:  # ignoring uncondition's own input mask (the round-1 defect) must be visible too
+        same_mask = dit_oracle.denoise_step(
+            lambda x, t, c: dit_oracle.forward(sd, cfg, x, inp["cond_mask"], inp["pose"] if c else None, inp["padding"], t,
+                                               inp["ctx_c"] if c else inp["ctx_u"]),
+            inp["x"], inp["gt"], noise, ind, sigma, sigma_next, guidance, return_net_output=True)[1]
+        assert rel(same_mask, want_o) > 2 * tol
 
 
 def test_engine_errors_are_loud():
@@ -112,8 +150,10 @@ def test_engine_errors_are_loud():
 
 
 def test_sampler_loop_matches_oracle_loop():
-    """Three steps of generate_samples_from_batch (D1) on the tiny net against the oracle loop: conditions assembled by
-    the host mirrors (D12), loop body = g3c_denoise_step."""
+    """Four steps of generate_samples_from_batch (D1) on the tiny net against the oracle loop: conditions assembled by
+    the host mirrors (D12) with add_input_frames_guidance (uncondition carries its own all-zero input mask), loop body =
+    g3c_denoise_step.  The 4-step Karras schedule ends at sigma -> 0, where x is the network's x0 prediction; negative
+    controls: the oracle loop with swapped branches / without guidance misses the tolerance by >= 5x."""
     from gen3c_b200 import model_gen3c as mg
 
     cfg, shp = cases.TINY, cases.TINY_SHAPE
@@ -122,27 +162,37 @@ def test_sampler_loop_matches_oracle_loop():
     net = build_net(cfg, sd)
     inp = cases.dit_inputs(cfg, **shp)
     bf = torch.bfloat16
-    steps, guidance = 3, 1.0
+    steps, guidance = 4, 2.0
     xt0 = (torch.randn(1, 16, T, H, W, generator=torch.Generator().manual_seed(9)) * 80.0).to(bf)
     cond = mg.VideoExtendCondition(crossattn_emb=inp["ctx_c"][None].cuda(), padding_mask=torch.zeros(1, 1, H * 8, W * 8).cuda(),
                                    fps=torch.tensor([24.0]), video_cond_bool=True)
     unc = mg.VideoExtendCondition(crossattn_emb=inp["ctx_u"][None].cuda(), padding_mask=cond.padding_mask,
-                                  fps=cond.fps, video_cond_bool=True)
+                                  fps=cond.fps, video_cond_bool=False)   # add_input_frames_guidance=True
     lat = inp["gt"][None].cuda().to(bf)
     cond = mg.add_condition_pose(inp["pose"][None].cuda().to(bf), mg.add_condition_video_indicator_and_video_input_mask(lat, cond, 1))
     unc = mg.add_condition_pose(inp["pose"][None].cuda().to(bf), mg.add_condition_video_indicator_and_video_input_mask(lat, unc, 1), True)
+    assert float(unc.condition_video_input_mask.abs().max()) == 0.0 and float(cond.condition_video_input_mask.max()) == 1.0
     got = mg.generate_samples_from_batch(net, cond, unc, guidance=guidance, seed=1, state_shape=(16, T, H, W),
                                          num_steps=steps, xt0=xt0)[0].float().cpu()
     sig = dit_oracle.karras_sigmas(steps)
     noise = torch.from_numpy(dit_oracle.arch_invariant_rand((1, 16, T, H, W), 1))[0]
     ind = torch.zeros(T)
     ind[0] = 1.0
+    zero_mask = torch.zeros_like(inp["cond_mask"])
 
-    def onet(x_in, t, c):
-        return dit_oracle.forward(sd, cfg, x_in, inp["cond_mask"], inp["pose"] if c else None, inp["padding"], t,
-                                  inp["ctx_c"] if c else inp["ctx_u"])
+    def loop(swap=False, g=guidance):
+        def onet(x_in, t, c):
+            c = c != swap
+            return dit_oracle.forward(sd, cfg, x_in, inp["cond_mask"] if c else zero_mask, inp["pose"] if c else None,
+                                      inp["padding"], t, inp["ctx_c"] if c else inp["ctx_u"])
 
-    x = xt0[0].float()
-    for i in range(steps):
-        x = dit_oracle.denoise_step(onet, x, inp["gt"], noise, ind, float(sig[i]), float(sig[i + 1]), guidance)
-    assert rel(got, x) < 1e-2, rel(got, x)
+        x = xt0[0].float()
+        for i in range(steps):
+            x = dit_oracle.denoise_step(onet, x, inp["gt"], noise, ind, float(sig[i]), float(sig[i + 1]), g)
+        return x
+
+    want = loop()
+    tol = 1e-2
+    assert rel(got, want) < tol, rel(got, want)
+    # negative controls: swapped branches 0.14, guidance ignored 0.055 (measured on the oracle)
+    assert rel(loop(swap=True), want) > 5 * tol and rel(loop(g=0.0), want) > 5 * tol

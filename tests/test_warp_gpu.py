@@ -125,8 +125,6 @@ def test_full_size_identity_roundtrip():
     assert float((pix[0, :, 0] - pair).abs().max()) <= 1e-5
 
 
-@pytest.mark.skipif(os.environ.get("G3C_EXPERIMENTAL_FOREGROUND", "0") != "1",
-                    reason="foreground-masking pass (SURVEY.md 8f rank 1) is opt-in until validated on hardware")
 def test_foreground_masking_matches_reference_golden(golden_dir):
     """forward_warp(foreground_masking=True): the native occlusion pass against the golden minted from the reference's
     own forward_warp (tests/golden/warp_R7_foreground.npz).  Occlusion decisions may flip only on knife-edge pixels
@@ -149,6 +147,42 @@ def test_foreground_masking_matches_reference_golden(golden_dir):
     assert close_frac(d[same[:, 0]], g["depth"][same[:, 0]], 1e-3) > 0.999
 
 
+def test_foreground_masking_full_size_properties():
+    """704x1280 (BASELINE frame size; the brute-force oracle would need 1e11 ray/triangle tests): a near box in front of a
+    smooth background, camera shifted.  Size-independent properties of the occlusion pass: it only ever REMOVES pixels;
+    every removed pixel was background (splatted depth well behind the box); everything else is bit-identical to the
+    plain warp; and the cache-level path (g3c_render_cache + g3c_render_cache_occlusion through Cache3D_Base) returns
+    exactly what forward_warp(foreground_masking=True) returns for the same frame."""
+    from gen3c_b200 import warp
+    from gen3c_b200.cache_3d import Cache3D_Base
+
+    h, w = 704, 1280
+    depth = (2.9 + 0.35 * cases.smooth_depth(h, w)).astype(np.float32)
+    depth[220:520, 440:840] = 1.2
+    g = torch.Generator(device="cuda").manual_seed(0)
+    img = torch.rand(1, 3, h, w, device="cuda", generator=g) * 2 - 1
+    K = cu(cases.intrinsics(h, w)[None])
+    eye = torch.eye(4, device="cuda")[None]
+    tgt = cu(cases.look(0.06, -0.015, (0.12, 0.01, 0.03))[None])
+    d = cu(depth[None, None])
+    pts = warp.unproject_points(d, eye, K)
+    boundary = ~warp.reliable_depth_mask_range_batch(d)[:, 0]
+    assert 1e-4 < float(boundary.float().mean()) < 0.05
+    w0, m0, z0, _ = warp.forward_warp(img, None, None, None, tgt, K, K, render_depth=True, world_points1=pts)
+    w1, m1, z1, _ = warp.forward_warp(img, None, None, None, tgt, K, K, world_points1=pts, foreground_masking=True,
+                                      boundary_mask=boundary)
+    removed = (m0 > 0) & (m1 == 0)
+    assert bool(((m1 > 0) <= (m0 > 0)).all())                     # never adds coverage
+    assert float(removed.float().mean()) > 1e-3                   # the box edge does occlude something
+    assert float(z0[removed[:, 0]].min()) > 1.2 + 0.02            # only background goes
+    keep = ~removed
+    assert torch.equal(w1[keep.expand_as(w1)], w0[keep.expand_as(w0)]) and torch.equal(z1[keep[:, 0]], z0[keep[:, 0]])
+    assert float(w1[removed.expand_as(w1)].max()) == -1.0 and float(z1[removed[:, 0]].max()) == 0.0
+    cache = Cache3D_Base(input_image=img, input_depth=d, input_w2c=eye, input_intrinsics=K, foreground_masking=True)
+    pix, msk = cache.render_cache(tgt[None], K[None])
+    assert torch.equal(msk[0, 0], m1[0][None]) and torch.equal(pix[0, 0, 0], w1[0])
+
+
 def test_error_behaviour():
     from gen3c_b200 import warp
 
@@ -156,9 +190,13 @@ def test_error_behaviour():
     with pytest.raises(AssertionError):
         warp.forward_warp(img, None, None, None, torch.eye(4, device="cuda")[None], None, None,
                           world_points1=torch.zeros(1, 8, 8, 3, device="cuda"))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(AssertionError):   # foreground_masking without a boundary mask (reference :286)
         warp.forward_warp(img, None, None, None, torch.eye(4, device="cuda")[None], None,
                           torch.eye(3, device="cuda")[None], world_points1=torch.zeros(1, 8, 8, 3, device="cuda"),
                           foreground_masking=True)
+    with pytest.raises(NotImplementedError):
+        warp.forward_warp(img, None, None, None, torch.eye(4, device="cuda")[None], None,
+                          torch.eye(3, device="cuda")[None], world_points1=torch.zeros(1, 8, 8, 3, device="cuda"),
+                          cameraray_filtering=True)
     with pytest.raises(AssertionError):
         warp.reliable_depth_mask_range_batch(torch.ones(1, 1, 8, 8, device="cuda"), window_size=4)
