@@ -35,6 +35,9 @@
 namespace g3c {
 namespace v1 {
 
+#ifndef G3C_ATTN_POLY_DEFAULT
+#define G3C_ATTN_POLY_DEFAULT 0  // fraction 1/n of the exponential pairs on the FMA pipe in the default path (0 = none)
+#endif
 constexpr int ATT_THREADS = 320;
 constexpr int ATT_TILE = 128;             // rows per Q tile, keys per KV tile, head dim
 constexpr int ATT_HALF_BYTES = 128 * 128; // one 64-column half of a 128x128 bf16 tile
@@ -84,6 +87,32 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {  // FADD2: t
   uint64_t r;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
+}
+
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {  // FFMA2: two fp32 fmas in one instruction
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// 2^x for a PAIR of scores on the FMA pipe, packed fp32x2 arithmetic (FA4-style MUFU offload): round-to-nearest split
+// by the magic-number add, degree-3 minimax polynomial on [-0.5, 0.5] (rel. err 7.5e-5, far below the bf16 rounding of
+// P), exponent inserted with one shift-add per element.  8 FMA-pipe / ALU instructions per pair against 2 MUFU slots of
+// 8 clk each: the 16 ex2/clk/SM MUFU is as slow as the two MMAs of a KV step, so moving a fraction of the exponentials
+// here takes the softmax off the tensor pipe's critical path.
+__device__ __forceinline__ void ex2_poly2(float xa, float xb, float& ya, float& yb) {
+  const uint64_t magic = pack2(12582912.0f, 12582912.0f);  // 1.5 * 2^23
+  const uint64_t x = pack2(fmaxf(xa, -125.0f), fmaxf(xb, -125.0f));
+  const uint64_t xr = fadd2(x, magic);                                           // low mantissa bits = round(x)
+  const uint64_t n = fadd2(xr, pack2(-12582912.0f, -12582912.0f));
+  const uint64_t f = ffma2(n, pack2(-1.0f, -1.0f), x);                           // x - n in [-0.5, 0.5]
+  uint64_t pl = ffma2(pack2(0.05517165f, 0.05517165f), f, pack2(0.24261113f, 0.24261113f));
+  pl = ffma2(pl, f, pack2(0.69326097f, 0.69326097f));
+  pl = ffma2(pl, f, pack2(0.99992806f, 0.99992806f));
+  float pa, pb, ra, rb;
+  unpack2(pl, pa, pb);
+  unpack2(xr, ra, rb);
+  ya = __int_as_float(__float_as_int(pa) + (__float_as_int(ra) << 23));
+  yb = __int_as_float(__float_as_int(pb) + (__float_as_int(rb) << 23));
 }
 
 // 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, rel. err 7.5e-5, far below the bf16
@@ -345,7 +374,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         const float xa = fmaf(__uint_as_float(sv[2 * i]), c, neg);
         const float xb = fmaf(__uint_as_float(sv[2 * i + 1]), c, neg);
         const float a = ex2_approx(xa);
-        const float b = (kPolyEvery > 0 && (i % (kPolyEvery / 2 > 0 ? kPolyEvery / 2 : 1)) == 0) ? ex2_poly(xb) : ex2_approx(xb);
+        const float b = ex2_approx(xb);
         ls[(2 * i) & 3] += a;
         ls[(2 * i + 1) & 3] += b;
         pk[i] = pack_bf16x2(a, b);
@@ -443,7 +472,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         auto exp64p = [&]() {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float a = ex2_approx(__uint_as_float(s[2 * i])), b = ex2_approx(__uint_as_float(s[2 * i + 1]));
+            float a, b;
+            // kPolyEvery = n > 0: every n-th PAIR of exponentials runs on the FMA pipe (packed polynomial)
+            if (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == (kPolyEvery > 0 ? kPolyEvery - 1 : 0)) {
+              ex2_poly2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]), a, b);
+            } else {
+              a = ex2_approx(__uint_as_float(s[2 * i]));
+              b = ex2_approx(__uint_as_float(s[2 * i + 1]));
+            }
             ls2[i & 1] = fadd2(ls2[i & 1], pack2(a, b));
             pk[i] = pack_bf16x2(a, b);
           }
@@ -581,7 +617,12 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
   static int poly = -1, mode = 2, cluster = 1;
   if (poly < 0) {
     const char* e = getenv("G3C_ATTN_POLY");
-    poly = (e && atoi(e) != 0) ? 4 : 0;
+    poly = e ? atoi(e) : G3C_ATTN_POLY_DEFAULT;
+    if (poly != 0 && poly != 2 && poly != 3 && poly != 4 && poly != 6) poly = 4;
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<2, 0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<3, 0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<4, 0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<6, 0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     e = getenv("G3C_ATTN_MODE");
     mode = e ? (atoi(e) != 0 ? 2 : 0) : 2;
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
@@ -627,8 +668,6 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     // also the choice for short key ranges (cross-attention: 4 KV tiles): the CTA is prologue-bound there and the
     // cluster launch / second-pass agreement of the default path only add latency (0.72 vs 0.83 ms at 56 320 x 512)
     k_attn_fwd<0, 0, 0, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
-  } else if (poly) {
-    k_attn_fwd<4, 0, 2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
   } else if (cluster && (grid.x % 2 == 0 || grid.x < 16)) {
     // CTA pairs along the query dimension sharing every K / V tile through TMA multicast.  An odd number of query
     // blocks would need a padding CTA (zero-filled Q rows, stores nothing): worth it only for small grids, where it
@@ -645,7 +684,15 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 0, 2, true>, tmQ, tmK, tmV, p));
+    switch (poly) {  // fraction of the exponentials on the FMA pipe: 1/2, 1/3, 1/4, 1/6 of the pairs, or none
+      case 2: G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<2, 0, 2, true>, tmQ, tmK, tmV, p)); break;
+      case 3: G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<3, 0, 2, true>, tmQ, tmK, tmV, p)); break;
+      case 4: G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<4, 0, 2, true>, tmQ, tmK, tmV, p)); break;
+      case 6: G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<6, 0, 2, true>, tmQ, tmK, tmV, p)); break;
+      default: G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 0, 2, true>, tmQ, tmK, tmV, p));
+    }
+  } else if (poly) {
+    k_attn_fwd<4, 0, 2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
   } else {
     k_attn_fwd<0, 0, 2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
   }

@@ -15,6 +15,8 @@
 //                           4 x red.global.add.v4.f32 {r*w, g*w, b*w, w} per source pixel
 //   pass 3  k_normalise   : crop the 1-px ring, acc/w, fill, clamp, write planar outputs
 // HBM-bound by design: algorithmic traffic 44 B/px.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace g3c {
@@ -203,6 +205,114 @@ __global__ void __launch_bounds__(256)
     SplatIdx s = splat_indices(fx, fy, x, y, W, H);
     float v0 = img[i], v1 = C > 1 ? img[HW + i] : 0.0f, v2 = C > 2 ? img[2 * HW + i] : 0.0f;
     splat_pixel(a, az, s, qz, lz_max, m, v0, v1, v2, W);
+  }
+}
+
+// ---- fast variant (default): 4 consecutive source pixels per thread, merged destinations, cheaper weight arithmetic ----
+// The round-1 kernel was issue / atomic bound (ncu: XU 42 %, L2 47 %, DRAM 17 %): 7 IEEE divisions + expf + log1pf per
+// pixel and 4 vector reds.  Here:
+//  * per pixel 2 IEEE divisions (the projected coordinates: their floor / ceil pick the destination, kept exact), one
+//    LG2, one EX2, one RCP: dw = exp(50 lz / lzmax) is inverted once (rcp.approx, 1 ulp) and multiplies the four
+//    bilinear weights; 50 / (lzmax + 1e-7) is a per-item constant; log1p(z) = lg2(1 + z) ln 2 — absolute error
+//    2.4e-7, i.e. 1e-5 relative on a weight, far inside the parity tolerance (the weights are normalised away);
+//  * a thread walks 4 neighbouring source pixels of one row and keeps one pending destination per output row in
+//    registers: under a smooth warp the north-east corner of pixel j is the north-west corner of pixel j+1, so a thread
+//    issues ~10 vector reds for 4 pixels instead of 16 (contributions to the same texel are added in registers first).
+struct Pending {
+  long long idx;  // texel index in the padded accumulator, -1 = empty
+  float a, b, c, w, z;
+};
+__device__ __forceinline__ void pend_flush(const Pending& p, float* __restrict__ acc, float* __restrict__ accz) {
+  if (p.idx >= 0) {
+    red_add_v4(acc + 4 * p.idx, p.a, p.b, p.c, p.w);
+    if (accz) atomicAdd(accz + p.idx, p.z);
+  }
+}
+__device__ __forceinline__ void pend_add(Pending& p, long long idx, float wt, float v0, float v1, float v2, float z,
+                                         float* __restrict__ acc, float* __restrict__ accz) {
+  if (wt == 0.0f) return;  // a zero weight adds +0 to every slot (identical result for finite inputs)
+  if (idx == p.idx) {
+    p.a += v0 * wt; p.b += v1 * wt; p.c += v2 * wt; p.w += wt; p.z += z * wt;
+  } else {
+    pend_flush(p, acc, accz);
+    p.idx = idx; p.a = v0 * wt; p.b = v1 * wt; p.c = v2 * wt; p.w = wt; p.z = z * wt;
+  }
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(256)
+    k_splat_points4(const float* __restrict__ points, const float* __restrict__ image,
+                    const float* __restrict__ mask, const float* __restrict__ w2c,
+                    const float* __restrict__ K, ItemMap map, int item0, int C, int H, int W,
+                    int group, const float* __restrict__ gmax, float* __restrict__ acc,
+                    float* __restrict__ accz, float* __restrict__ flow_out) {
+  const int HW = H * W, Wq = W >> 2, nq = H * Wq;
+  const int item = item0 + blockIdx.y;
+  const int src = map.src(item);
+  const Cam c = load_cam(w2c + 16 * map.cam(item), K + 9 * map.cam(item));
+  const float4* p4 = reinterpret_cast<const float4*>(points + (size_t)src * HW * 3);
+  const float* img = image + (size_t)src * C * HW;
+  const float* msk = mask ? mask + (size_t)src * HW : nullptr;
+  const float escale = __fdiv_rn(50.0f, __fadd_rn(gmax[item / group], 1e-7f));
+  float* a = acc + (size_t)blockIdx.y * (H + 2) * (W + 2) * 4;
+  float* az = accz ? accz + (size_t)blockIdx.y * (H + 2) * (W + 2) : nullptr;
+  const int Wp = W + 2;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+    const int y = q / Wq, x0 = (q - y * Wq) * 4;
+    const int i0 = y * W + x0;
+    // 4 points = 12 floats = 3 aligned float4 (i0 is a multiple of 4)
+    const float4 pa = p4[(i0 * 3) / 4], pb = p4[(i0 * 3) / 4 + 1], pc = p4[(i0 * 3) / 4 + 2];
+    const float px[4] = {pa.x, pa.w, pb.z, pc.y}, py[4] = {pa.y, pb.x, pb.w, pc.z}, pz[4] = {pa.z, pb.y, pc.x, pc.w};
+    const float4 r4 = *reinterpret_cast<const float4*>(img + i0);
+    const float4 g4 = C > 1 ? *reinterpret_cast<const float4*>(img + HW + i0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 b4 = C > 2 ? *reinterpret_cast<const float4*>(img + 2 * HW + i0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 m4 = msk ? *reinterpret_cast<const float4*>(msk + i0) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float v0[4] = {r4.x, r4.y, r4.z, r4.w}, v1[4] = {g4.x, g4.y, g4.z, g4.w}, v2[4] = {b4.x, b4.y, b4.z, b4.w};
+    const float mk[4] = {m4.x, m4.y, m4.z, m4.w};
+    Pending top{-1, 0.f, 0.f, 0.f, 0.f, 0.f}, bot{-1, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float fxs[4], fys[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int x = x0 + j;
+      float qx, qy, qz;
+      project(c, px[j], py[j], pz[j], qx, qy, qz);
+      const float m = mk[j] * (qz > 0.0f ? 1.0f : 0.0f);
+      const float den = __fadd_rn(qz, 1e-7f);
+      const float fx = __fsub_rn(__fdiv_rn(qx, den), (float)x);
+      const float fy = __fsub_rn(__fdiv_rn(qy, den), (float)y);
+      fxs[j] = fx;
+      fys[j] = fy;
+      const SplatIdx s = splat_indices(fx, fy, x, y, W, H);
+      const float dyf = __fsub_rn(1.0f, __fsub_rn(s.py, (float)s.fy));
+      const float dyc = __fsub_rn(1.0f, __fsub_rn((float)s.cy, s.py));
+      const float dxf = __fsub_rn(1.0f, __fsub_rn(s.px, (float)s.fx));
+      const float dxc = __fsub_rn(1.0f, __fsub_rn((float)s.cx, s.px));
+      const float zc = fmaxf(qz, 0.0f);
+      const float lz = __log2f(1.0f + zc) * 0.6931471805599453f;
+      const float e = fminf(lz * escale, 80.0f);
+      // m / (exp(e) + 1e-7); NaN depths propagate like the reference's (NaN weights, nan_to_num in the normalise pass)
+      const float rdw = m * rcp_approx(__fadd_rn(ex2_fast(e * 1.4426950408889634f), 1e-7f));
+      const long long rt = (long long)s.fy * Wp, rb = (long long)s.cy * Wp;
+      pend_add(top, rt + s.fx, dyf * dxf * rdw, v0[j], v1[j], v2[j], qz, a, az);
+      pend_add(top, rt + s.cx, dyf * dxc * rdw, v0[j], v1[j], v2[j], qz, a, az);
+      pend_add(bot, rb + s.fx, dyc * dxf * rdw, v0[j], v1[j], v2[j], qz, a, az);
+      pend_add(bot, rb + s.cx, dyc * dxc * rdw, v0[j], v1[j], v2[j], qz, a, az);
+    }
+    pend_flush(top, a, az);
+    pend_flush(bot, a, az);
+    if (flow_out) {
+      *reinterpret_cast<float4*>(flow_out + ((size_t)item * 2) * HW + i0) = make_float4(fxs[0], fxs[1], fxs[2], fxs[3]);
+      *reinterpret_cast<float4*>(flow_out + ((size_t)item * 2 + 1) * HW + i0) = make_float4(fys[0], fys[1], fys[2], fys[3]);
+    }
   }
 }
 
@@ -739,9 +849,21 @@ static int render_items(g3c_render* r, const float* points, const float* image, 
     int n = n_items - i0 < r->max_items ? n_items - i0 : r->max_items;
     G3C_CUDA(cudaMemsetAsync(r->acc, 0, plane * 4 * sizeof(float) * n, st));
     if (want_depth) G3C_CUDA(cudaMemsetAsync(r->accz, 0, plane * sizeof(float) * n, st));
-    k_splat_points<<<px_grid(HW, n), 256, 0, st>>>(points, image, mask, w2c, K, map, i0, C, H, W,
-                                                   group, r->gmax, r->acc,
-                                                   want_depth ? r->accz : nullptr, flow_out);
+    // G3C_SPLAT=ref: the round-1 one-pixel-per-thread kernel with the reference's exact weight arithmetic (A/B runs)
+    static int fast = -1;
+    if (fast < 0) {
+      const char* e = getenv("G3C_SPLAT");
+      fast = !(e && e[0] == 'r');
+    }
+    const bool aligned = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(points) | reinterpret_cast<uintptr_t>(image) |
+                                           reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(flow_out)) % 16 == 0);
+    if (fast && aligned)
+      k_splat_points4<<<px_grid(HW / 4, n), 256, 0, st>>>(points, image, mask, w2c, K, map, i0, C, H, W, group, r->gmax,
+                                                          r->acc, want_depth ? r->accz : nullptr, flow_out);
+    else
+      k_splat_points<<<px_grid(HW, n), 256, 0, st>>>(points, image, mask, w2c, K, map, i0, C, H, W,
+                                                     group, r->gmax, r->acc,
+                                                     want_depth ? r->accz : nullptr, flow_out);
     k_normalise<<<px_grid(HW, n), 256, 0, st>>>(r->acc, want_depth ? r->accz : nullptr, i0, C, H,
                                                 W, is_image, out, mask_out,
                                                 want_depth ? depth_out : nullptr);

@@ -156,3 +156,72 @@ def generate_samples_from_batch(net: VideoExtendGeneralDIT, condition: VideoExte
     if net.is_context_parallel_enabled:
         samples = cat_outputs_cp(samples, seq_dim=2, cp_group=net.cp_group)
     return samples
+
+
+class DiffusionGen3CModel:
+    """The reference's model object (model_gen3c.py:26-139 over model_v2w.py / model_t2w.py) reduced to what inference
+    touches: `net`, `tokenizer`, `encode` / `decode`, `state_shape`, `frame_buffer_max`, `chunk_size`,
+    `_get_conditions` and `generate_samples_from_batch` with the reference's signatures.  GEN3C_Cosmos_7B is the one
+    configuration (config/inference/cosmos-1-diffusion-gen3c.py:22-46): frame_buffer_max 2, sigma_data 0.5, latent
+    [16, 16, 88, 160], 121-frame tokenizer chunks."""
+
+    def __init__(self, net: Optional[VideoExtendGeneralDIT] = None, tokenizer=None, frame_buffer_max: int = 2,
+                 sigma_data: float = 0.5, state_shape=(16, 16, 88, 160), device="cuda"):
+        self.device = torch.device(device)
+        self.net = net
+        self.tokenizer = tokenizer
+        self.frame_buffer_max = frame_buffer_max
+        self.chunk_size = 121
+        self.sigma_data = sigma_data
+        self.state_shape = list(state_shape)
+        self.tensor_kwargs = {"device": self.device, "dtype": torch.bfloat16}
+        self.cp_group = None   # set by the caller together with net.enable_context_parallel
+
+    # model_t2w.py: encode / decode scale by sigma_data
+    @torch.no_grad()
+    def encode(self, state: torch.Tensor) -> torch.Tensor:
+        return self.tokenizer.encode(state) * self.sigma_data
+
+    @torch.no_grad()
+    def decode(self, latent: torch.Tensor) -> torch.Tensor:
+        return self.tokenizer.decode(latent / self.sigma_data)
+
+    def encode_warped_frames(self, condition_state, condition_state_mask, dtype):
+        return encode_warped_frames(condition_state, condition_state_mask, self.encode, self.frame_buffer_max, dtype)
+
+    def _get_conditions(self, data_batch: dict, is_negative_prompt: bool = False,
+                        condition_latent: Optional[torch.Tensor] = None, num_condition_t: Optional[int] = None,
+                        add_input_frames_guidance: bool = False):
+        """reference :59-113.  Without a negative prompt the unconditional text context is zeros (the conditioner's
+        dropout of the text embedding, conditioner.py get_condition_uncondition)."""
+        ctx = data_batch["t5_text_embeddings"]
+        if is_negative_prompt:  # conditioner.py:267-292: falls back to the prompt itself when no negative embedding is given
+            neg = data_batch.get("neg_t5_text_embeddings", ctx)
+        else:                   # conditioner.py:234-265: the text embedder is dropped out (zeros)
+            neg = torch.zeros_like(ctx)
+        cond, uncond = get_conditions(ctx, neg, data_batch.get("padding_mask"), data_batch["condition_state"],
+                                      data_batch["condition_state_mask"], condition_latent, num_condition_t, self.encode,
+                                      self.frame_buffer_max, add_input_frames_guidance, data_batch.get("fps"),
+                                      self.tensor_kwargs["dtype"])
+        if self.net.is_context_parallel_enabled:
+            from .parallel import broadcast_condition
+
+            cond = broadcast_condition(cond, cp_group=self.net.cp_group)
+            uncond = broadcast_condition(uncond, cp_group=self.net.cp_group)
+        return cond, uncond
+
+    @torch.no_grad()
+    def generate_samples_from_batch(self, data_batch: dict, guidance: float = 1.5, seed: int = 1, state_shape=None,
+                                    n_sample: Optional[int] = 1, is_negative_prompt: bool = False, num_steps: int = 35,
+                                    condition_latent: Optional[torch.Tensor] = None,
+                                    num_condition_t: Optional[int] = None, condition_augment_sigma: float = None,
+                                    add_input_frames_guidance: bool = False) -> torch.Tensor:
+        """reference model_v2w.py:84-155."""
+        assert condition_latent is not None, "condition_latent should be provided"
+        if n_sample not in (None, 1):
+            raise NotImplementedError("the native loop body handles one sample per call (GEN3C inference uses n_sample=1)")
+        cond, uncond = self._get_conditions(data_batch, is_negative_prompt, condition_latent, num_condition_t,
+                                            add_input_frames_guidance)
+        return generate_samples_from_batch(self.net, cond, uncond, guidance=guidance, seed=seed,
+                                           state_shape=tuple(state_shape or self.state_shape), num_steps=num_steps,
+                                           condition_augment_sigma=condition_augment_sigma, sigma_data=self.sigma_data)

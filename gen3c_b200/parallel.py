@@ -26,3 +26,45 @@ def cat_outputs_cp(x: torch.Tensor, seq_dim: int, cp_group) -> torch.Tensor:
     parts = [torch.empty_like(x) for _ in range(size)]
     dist.all_gather(parts, x.contiguous(), group=cp_group)
     return torch.cat(parts, dim=seq_dim)
+
+
+def _robust_broadcast(tensor: torch.Tensor, src: int, pg) -> torch.Tensor:
+    """reference parallel.py:136-163: broadcast the shape first so that receivers may hold a tensor of any shape."""
+    dev = tensor.device
+    if dist.get_rank() == src:
+        shape = torch.tensor(tensor.shape, device=dev)
+    else:
+        shape = torch.empty(tensor.dim(), dtype=torch.long, device=dev)
+    dist.broadcast(shape, src, group=pg)
+    if dist.get_rank() != src:
+        tensor = tensor.new_empty(shape.tolist()).type_as(tensor)
+    tensor = tensor.contiguous()
+    dist.broadcast(tensor, src, group=pg)
+    return tensor
+
+
+def broadcast(item, cp_group=None):
+    """reference parallel.py:90-133 for the context-parallel group (there is no tensor parallelism in GEN3C
+    inference): the item of the group's lowest global rank replaces everybody's."""
+    if cp_group is None or not dist.is_initialized() or dist.get_world_size(cp_group) <= 1:
+        return item
+    src = min(dist.get_process_group_ranks(cp_group))
+    if isinstance(item, torch.Tensor):
+        return _robust_broadcast(item, src, cp_group)
+    if item is not None:
+        box = [item]
+        dist.broadcast_object_list(box, src, group=cp_group)
+        item = box[0]
+    return item
+
+
+def broadcast_condition(condition, to_tp: bool = True, to_cp: bool = True, cp_group=None):
+    """reference model_v2w.py broadcast_condition: every tensor / picklable field of the condition object is replaced by
+    rank-min's copy, so that all context-parallel ranks denoise against identical conditions."""
+    if not to_cp or cp_group is None:
+        return condition
+    for key, value in list(vars(condition).items()):
+        if key == "extra":
+            continue
+        setattr(condition, key, broadcast(value, cp_group))
+    return condition

@@ -138,3 +138,51 @@ def dit_inputs(cfg: DitCfg, T: int, H: int, W: int, ctx_len: int, seed: int = 1,
     timestep = float(torch.tensor(0.734375))  # exactly representable in bf16
     return dict(x=x, cond_mask=cond_mask, pose=pose, padding=padding, ctx_c=ctx_c, ctx_u=ctx_u, gt=gt,
                 timestep=timestep)
+
+
+# --------------------------------------------------------------------------------------------------
+# a tiny TorchScript tokenizer checkpoint (encoder.jit / decoder.jit / mean_std.pt) for the VAE-wrapper tests
+# --------------------------------------------------------------------------------------------------
+class _TinyEnc(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        g = torch.Generator().manual_seed(3)
+        self.w = torch.nn.Parameter(torch.randn(16, 3, generator=g))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:  # [B,3,1+8k,H,W] -> [B,16,1+k,H/8,W/8]
+        b0, c0, t0, h0, w0 = x.shape
+        xs = x.reshape(b0, c0, t0, h0 // 8, 8, w0 // 8, 8).mean(6).mean(4)
+        first, rest = xs[:, :, :1], xs[:, :, 1:]
+        b, c, t, h, w = rest.shape
+        rest = rest.reshape(b, c, t // 8, 8, h, w).mean(3)
+        return torch.einsum("oc,bcthw->bothw", self.w, torch.cat([first, rest], 2))
+
+
+class _TinyDec(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        g = torch.Generator().manual_seed(4)
+        self.w = torch.nn.Parameter(torch.randn(3, 16, generator=g) * 0.3)
+
+    def forward(self, z: torch.Tensor) -> torch.Tensor:  # [B,16,1+k,h,w] -> [B,3,1+8k,8h,8w]
+        rgb = torch.einsum("oc,bcthw->bothw", self.w, z)
+        t = torch.cat([rgb[:, :, :1], rgb[:, :, 1:].repeat_interleave(8, dim=2)], 2)
+        return torch.nn.functional.interpolate(t, scale_factor=(1.0, 8.0, 8.0), mode="nearest")
+
+
+def write_tiny_tokenizer(vae_dir: str) -> None:
+    """encoder.jit, decoder.jit, mean_std.pt in the layout of checkpoints/Cosmos-Tokenize1-CV8x8x8-720p."""
+    import os
+
+    os.makedirs(vae_dir, exist_ok=True)
+    torch.jit.script(_TinyEnc()).save(os.path.join(vae_dir, "encoder.jit"))
+    torch.jit.script(_TinyDec()).save(os.path.join(vae_dir, "decoder.jit"))
+    g = torch.Generator().manual_seed(5)
+    mean = torch.randn(16 * 16, generator=g) * 0.2
+    std = 0.5 + torch.rand(16 * 16, generator=g)
+    torch.save((mean, std), os.path.join(vae_dir, "mean_std.pt"))
+
+
+def tiny_tokenizer_video() -> torch.Tensor:
+    g = torch.Generator().manual_seed(6)
+    return (torch.rand(1, 3, 34, 16, 32, generator=g) * 2 - 1)  # two chunks of 17 frames

@@ -161,7 +161,7 @@ def rope_angles(cfg: DitCfg, T: int, Hp: int, Wp: int, fps: float, t0: int = 0, 
         eh[None, :, None, :].expand(T, Hp, Wp, -1),
         ew[None, None, :, :].expand(T, Hp, Wp, -1),
     ] * 2, dim=-1)
-    return em.reshape(T * Hp * Wp, dim).float()
+    return em.reshape(T * Hp * Wp, dim).float().to(device)
 
 
 def apply_rope(x: torch.Tensor, ang: torch.Tensor) -> torch.Tensor:

@@ -346,6 +346,36 @@ def mint_dit_fullwidth():
     return 0 if e < 1e-4 else 1
 
 
+def mint_tokenizer():
+    """The reference's VideoJITTokenizer (module/pretrained_vae.py:314-509) on a tiny TorchScript checkpoint
+    (oracle/cases.py::write_tiny_tokenizer) -> tests/golden/vae_wrapper.npz: chunked encode / decode, latent mean / std,
+    dtype handling (fp32 and bf16 modules), frame-count helpers."""
+    import tempfile
+
+    ref_stubs.install()
+    from cosmos_predict1.diffusion.module.pretrained_vae import VideoJITTokenizer
+
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        cases.write_tiny_tokenizer(d)
+        x = cases.tiny_tokenizer_video()
+        for tag, bf in (("f32", False), ("bf16", True)):
+            tok = VideoJITTokenizer(name="tiny", latent_ch=16, is_bf16=bf, spatial_compression_factor=8,
+                                    temporal_compression_factor=8, pixel_chunk_duration=17, max_enc_batch_size=1,
+                                    max_dec_batch_size=1)
+            tok.register_mean_std(d)
+            tok.load_decoder(d)
+            tok.load_encoder(d)
+            z = tok.encode(x)
+            y = tok.decode(z)
+            out[f"z_{tag}"], out[f"y_{tag}"] = z.float().numpy(), y.float().numpy()
+            out["frames"] = np.array([tok.get_latent_num_frames(1), tok.get_latent_num_frames(34), tok.get_pixel_num_frames(6),
+                                      tok.latent_chunk_duration])
+    np.savez_compressed(os.path.join(OUT, "vae_wrapper.npz"), **out)
+    print("== tokenizer wrapper golden written: latent", out["z_f32"].shape, "video", out["y_f32"].shape, "==")
+    return 0
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]
@@ -356,6 +386,8 @@ def main():
         rc |= mint_cache_classes()
     if not only or "dit" in only:
         rc |= mint_dit()
+    if not only or "tokenizer" in only:
+        rc |= mint_tokenizer()
     if not only or "fullwidth" in only:
         rc |= mint_dit_fullwidth()
     sys.exit(rc)

@@ -84,7 +84,7 @@ def test_buffer_noise_branch():
     p1, m1 = noisy.render_cache(w2cs, Ks)
     assert torch.equal(m0, m1)
     d = p1 - p0
-    assert float(d[:, :, 1].abs().max()) == 0.0
+    assert float(d[:, :, 1].abs().max()) < 1e-5   # two renders differ by the order of their float atomics only
     assert abs(float(d[:, :, 0].std()) - 0.25) < 0.01
 
 

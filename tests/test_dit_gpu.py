@@ -113,10 +113,14 @@ def test_denoise_step_matches_oracle(step_index, uncond_mask_zero):
                                sigma, sigma_next, guidance,
                                cond_mask_uncond=mask_u.cuda().to(bf) if uncond_mask_zero else None,
                                net_output=net_out).float().cpu()
-    tol, tol_x = 5e-3, 1e-3   # network output: bf16 engine vs fp32 oracle; x_{t-1}: north_star's 1e-3
+    # one forward: 5e-3 (bf16 engine vs fp32 oracle, as in the forward tests).  The CFG combination (1+g) c - g u adds
+    # the two independent forward errors with weights 1+g and g: sqrt((1+g)^2 + g^2) = 2.9 at g = 1.5.
+    # x_{t-1}: north_star's 1e-3.
+    tol, tol_x = 5e-3, 1e-3
+    tol_o = tol * math.sqrt((1 + guidance) ** 2 + guidance ** 2)
     e_out, e_x = rel(net_out.float().cpu(), want_o), rel(got, want)
     print(f"sigma {sigma:.3f}: net_output rel-L2 {e_out:.2e}, x_next rel-L2 {e_x:.2e}")
-    assert e_out < tol, e_out
+    assert e_out < tol_o, e_out
     assert e_x < tol_x, e_x
     # frame 0 is driven by gt_latent, not by the network (indicator = 1)
     assert rel(got[:, 0], want[:, 0]) < tol_x
@@ -133,7 +137,7 @@ def test_denoise_step_matches_oracle(step_index, uncond_mask_zero):
             lambda x, t, c: dit_oracle.forward(sd, cfg, x, inp["cond_mask"], inp["pose"] if c else None, inp["padding"], t,
                                                inp["ctx_c"] if c else inp["ctx_u"]),
             inp["x"], inp["gt"], noise, ind, sigma, sigma_next, guidance, return_net_output=True)[1]
-        assert rel(same_mask, want_o) > 2 * tol
+        assert rel(same_mask, want_o) > 1.2 * tol_o
 
 
 def test_engine_errors_are_loud():

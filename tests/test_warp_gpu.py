@@ -176,11 +176,12 @@ def test_foreground_masking_full_size_properties():
     assert float(removed.float().mean()) > 1e-3                   # the box edge does occlude something
     assert float(z0[removed[:, 0]].min()) > 1.2 + 0.02            # only background goes
     keep = ~removed
-    assert torch.equal(w1[keep.expand_as(w1)], w0[keep.expand_as(w0)]) and torch.equal(z1[keep[:, 0]], z0[keep[:, 0]])
+    # (two separate splats: equal up to the order of their float atomics)
+    assert float((w1 - w0)[keep.expand_as(w1)].abs().max()) < 1e-4 and float((z1 - z0)[keep[:, 0]].abs().max()) < 1e-4
     assert float(w1[removed.expand_as(w1)].max()) == -1.0 and float(z1[removed[:, 0]].max()) == 0.0
     cache = Cache3D_Base(input_image=img, input_depth=d, input_w2c=eye, input_intrinsics=K, foreground_masking=True)
     pix, msk = cache.render_cache(tgt[None], K[None])
-    assert torch.equal(msk[0, 0], m1[0][None]) and torch.equal(pix[0, 0, 0], w1[0])
+    assert float((msk[0, 0] != m1[0][None]).float().mean()) < 1e-5 and float((pix[0, 0, 0] - w1[0]).abs().max()) < 1e-4
 
 
 def test_error_behaviour():
