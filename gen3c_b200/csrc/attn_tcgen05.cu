@@ -137,22 +137,34 @@ __device__ __forceinline__ float ex2_poly(float x) {
 //          The ~300 clk max reduction leaves the per-tile dependent chain (see the timeline in profiles/).
 // kCluster: the CTAs of two neighbouring query blocks of one head form a cluster; each TMA-loads HALF of every K / V
 //           tile and multicasts it into both CTAs' rings, so every K / V byte leaves L2 once per 512 query rows.
-template <int kPolyEvery, int kTrace, int kMode, bool kCluster>  // kTrace 1: stamps in every role, 2: MMA warp only
+// k2Cta:   (implies kCluster) the pair issues ONE 256-row UMMA per tile (`tcgen05.mma.cta_group::2`): tile t of the
+//           leader CTA and tile t of its peer share every S = Q K^T and P.V instruction.  Each CTA stages only HALF of
+//           the B operand — 64 of the 128 keys of a K tile, 64 of the 128 head dimensions of a V^T tile — so the
+//           shared-memory operand traffic of the tensor pipe and the TMA fill per SM are halved against the multicast
+//           variant (whose MMAs ran at ~82 % of their nominal rate: 1 388 clk per PV+S pair instead of 1 134, clock64
+//           timeline in profiles/r02_attn_trace.txt), and the ring holds 8 instead of 4 tiles in the same 128 KB.
+//           The leader's MMA thread issues for both SMs; `kv_full` / `p_half` / `q_full` live in the leader and collect
+//           both CTAs' arrivals, `s_full` / `kv_empty` are hit in both CTAs by multicast commits.
+template <int kPolyEvery, int kTrace, int kMode, bool kCluster, bool k2Cta = false>  // kTrace 1: stamps in every role, 2: MMA warp only
 __global__ void __launch_bounds__(ATT_THREADS, 1)
     k_attn_fwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  static_assert(!k2Cta || kCluster, "2-CTA MMAs need the cluster launch");
+  constexpr int kSlots = k2Cta ? 2 * ATT_SLOTS : ATT_SLOTS;            // ring entries (one K or V^T tile each)
+  constexpr int kSlotBytes = k2Cta ? ATT_TILE_BYTES / 2 : ATT_TILE_BYTES;  // this CTA's part of a tile
+  constexpr int kKvHalf = kSlotBytes / 2;                               // one 64-element K-dimension half of it
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_q = smem;                        // [2 tiles][2 halves][128 x 128 B]
-  uint8_t* smem_kv = smem + 2 * ATT_TILE_BYTES;  // [slots][2 halves][128 x 128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + ATT_SLOTS * ATT_TILE_BYTES);
+  uint8_t* smem_kv = smem + 2 * ATT_TILE_BYTES;  // [slots][2 halves][rows x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + kSlots * kSlotBytes);
   uint64_t* q_full = bars;                        // [1]
   uint64_t* kv_full = bars + 1;                   // [slots]
-  uint64_t* kv_empty = bars + 1 + ATT_SLOTS;      // [slots]
-  uint64_t* s_full = bars + 1 + 2 * ATT_SLOTS;    // [2]
-  uint64_t* p_half = bars + 3 + 2 * ATT_SLOTS;    // [tile][key half]: P columns of 64 keys stored
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7 + 2 * ATT_SLOTS);
+  uint64_t* kv_empty = bars + 1 + kSlots;         // [slots]
+  uint64_t* s_full = bars + 1 + 2 * kSlots;       // [2]
+  uint64_t* p_half = bars + 3 + 2 * kSlots;       // [tile][key half]: P columns of 64 keys stored
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7 + 2 * kSlots);
   uint32_t* redo_flag = tmem_ptr + 1;  // kMode 2: some row sum left the fp32 range, repeat in the exact mode
 
   const uint32_t warp = warp_id();
@@ -165,20 +177,25 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < ATT_SLOTS; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], kCluster ? 2 : 1);  // cluster: the slot is rewritten in both CTAs, both consumers release it
+    // 2-CTA: the leader's barrier collects its own expect_tx arrive and the peer's remote arrive (both CTAs' TMA bytes
+    // are credited to it); multicast variant: the slot is rewritten in both CTAs, both consumers release it
+    mbar_init(q_full, k2Cta ? 2 : 1);
+    for (int i = 0; i < kSlots; ++i) {
+      mbar_init(&kv_full[i], k2Cta ? 2 : 1);
+      mbar_init(&kv_empty[i], (kCluster && !k2Cta) ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_half[2 * i], 4);      // one elected arrive per softmax warp
-      mbar_init(&p_half[2 * i + 1], 4);
+      mbar_init(&p_half[2 * i], k2Cta ? 8 : 4);      // one elected arrive per softmax warp (of both CTAs)
+      mbar_init(&p_half[2 * i + 1], k2Cta ? 8 : 4);
     }
     *redo_flag = 0u;
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(tmem_ptr, 512);
+  if (warp == 9) {
+    if constexpr (k2Cta) tmem_alloc_2sm(tmem_ptr, 512);
+    else tmem_alloc(tmem_ptr, 512);
+  }
   tc_fence_before();
   __syncthreads();
   if constexpr (kCluster) cluster_sync_all();  // the peer's barriers exist before anything is multicast to them
@@ -197,13 +214,23 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     if (lane == 0) {
       // ===== TMA producer =====
       if (pass == 0) {
-        mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+        if constexpr (k2Cta) {
+          if (crank == 0) mbar_expect_tx(q_full, 4 * ATT_TILE_BYTES);  // both CTAs' two Q tiles
+          else mbar_arrive_leader(q_full);
+        } else {
+          mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+        }
 #pragma unroll
         for (int t = 0; t < 2; ++t)
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-            tma_load_2d(smem_q + t * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmQ, q_full,
-                        head * 128 + h * 64, q0 + t * ATT_TILE);
+          for (int h = 0; h < 2; ++h) {
+            if constexpr (k2Cta)
+              tma_load_2d_2sm(smem_q + t * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmQ, q_full, head * 128 + h * 64,
+                              q0 + t * ATT_TILE);
+            else
+              tma_load_2d(smem_q + t * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmQ, q_full,
+                          head * 128 + h * 64, q0 + t * ATT_TILE);
+          }
       }
       const int tiles_per_chunk = p.vt_chunk_len / ATT_TILE;
       const int n_chunks = p.Lk / p.vt_chunk_len;
@@ -228,42 +255,65 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         const int kv0 = chunk * p.vt_chunk_len + within * ATT_TILE;
         // K_j
         mbar_wait_ns(&kv_empty[slot], phase ^ 1, p.peer_timeout_ns);
-        mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
-        if constexpr (kCluster) {
+        if constexpr (k2Cta) {
+          // this CTA's 64 keys of the tile (box 64 x 64, both 64-dim halves); bytes credited to the leader's barrier
+          if (crank == 0) mbar_expect_tx(&kv_full[slot], 2 * kSlotBytes);
+          else mbar_arrive_leader(&kv_full[slot]);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d_2sm(smem_kv + slot * kSlotBytes + h * kKvHalf, &tmK, &kv_full[slot], head * 128 + h * 64,
+                            kv0 + (int)crank * 64);
+        } else if constexpr (kCluster) {
+          mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
           tma_load_2d_mc(smem_kv + slot * ATT_TILE_BYTES + crank * ATT_HALF_BYTES, &tmK, &kv_full[slot],
                          head * 128 + crank * 64, kv0, 3);
         } else {
+          mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
 #pragma unroll
           for (int h = 0; h < 2; ++h)
             tma_load_2d(smem_kv + slot * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmK, &kv_full[slot],
                         head * 128 + h * 64, kv0);
         }
-        if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; }
+        if (++slot == kSlots) { slot = 0; phase ^= 1; }
         // V_j  (transposed: rows = head dim, columns = keys)
         mbar_wait_ns(&kv_empty[slot], phase ^ 1, p.peer_timeout_ns);
-        mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
         const int koff = within * ATT_TILE;
-        if constexpr (kCluster) {
+        if constexpr (k2Cta) {
+          // this CTA's 64 head dimensions of the V^T tile, all 128 keys (two 64-key halves)
+          if (crank == 0) mbar_expect_tx(&kv_full[slot], 2 * kSlotBytes);
+          else mbar_arrive_leader(&kv_full[slot]);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            tma_load_3d_2sm(smem_kv + slot * kSlotBytes + h * kKvHalf, &tmV, &kv_full[slot], koff + h * 64,
+                            head * 128 + (int)crank * 64, chunk);
+        } else if constexpr (kCluster) {
+          mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
           tma_load_3d_mc(smem_kv + slot * ATT_TILE_BYTES + crank * ATT_HALF_BYTES, &tmV, &kv_full[slot],
                          koff + crank * 64, head * 128, chunk, 3);
         } else {
+          mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
 #pragma unroll
           for (int h = 0; h < 2; ++h)
             tma_load_3d(smem_kv + slot * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmV, &kv_full[slot],
                         koff + h * 64, head * 128, chunk);
         }
-        if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; }
+        if (++slot == kSlots) { slot = 0; phase ^= 1; }
       }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+    if (lane == 0 && (!k2Cta || crank == 0)) {
+      // ===== MMA issuer (2-CTA: one thread of the leader issues for both SMs) =====
+      constexpr uint32_t idesc = make_idesc_bf16(k2Cta ? 256 : 128, 128);
       const uint32_t tS[2] = {tmem_base, tmem_base + 128};
       const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
-      auto advance = [&]() { if (++slot == ATT_SLOTS) { slot = 0; phase ^= 1; } };
+      auto advance = [&]() { if (++slot == kSlots) { slot = 0; phase ^= 1; } };
+      auto commit = [&](uint64_t* bar) {   // s_full: seen by the softmax warps of every CTA the MMAs wrote to
+        if constexpr (k2Cta) umma_commit_2sm(bar);
+        else umma_commit(bar);
+      };
       auto release_slot = [&](uint32_t sl) {
-        if constexpr (kCluster) umma_commit_mc(&kv_empty[sl], 3);
+        if constexpr (k2Cta) umma_commit_2sm(&kv_empty[sl]);
+        else if constexpr (kCluster) umma_commit_mc(&kv_empty[sl], 3);
         else umma_commit(&kv_empty[sl]);
       };
       auto mma_s = [&](int t, uint32_t kslot) {
@@ -272,8 +322,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         for (int k = 0; k < 8; ++k) {
           const uint32_t half = k >> 2, off = (k & 3) * 32;
           uint64_t da = make_sdesc_sw128(smem_u32(smem_q + t * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
-          uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + kslot * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
-          umma_ss(tS[t], sdesc_advance(da, off), sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
+          uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + kslot * kSlotBytes + half * kKvHalf));
+          if constexpr (k2Cta) umma_ss_2sm(tS[t], sdesc_advance(da, off), sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
+          else umma_ss(tS[t], sdesc_advance(da, off), sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
         }
       };
       auto mma_pv = [&](int t, uint32_t vslot, bool first, int hh) {
@@ -282,8 +333,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         for (int kk = 0; kk < 4; ++kk) {
           const int k = hh * 4 + kk;
           const uint32_t half = k >> 2, off = (k & 3) * 32;
-          uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + vslot * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
-          umma_ts(tO[t], tS[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
+          uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + vslot * kSlotBytes + half * kKvHalf));
+          if constexpr (k2Cta) umma_ts_2sm(tO[t], tS[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
+          else umma_ts(tO[t], tS[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
         }
       };
       if (pass == 0) mbar_wait_ns(q_full, 0, p.peer_timeout_ns);
@@ -292,9 +344,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       uint32_t kslot = slot;
       advance();
       mma_s(0, kslot);
-      umma_commit(&s_full[0]);
+      commit(&s_full[0]);
       mma_s(1, kslot);
-      umma_commit(&s_full[1]);
+      commit(&s_full[1]);
       release_slot(kslot);
       for (int j = 0; j < n_kv; ++j) {
         const bool more = j + 1 < n_kv;
@@ -318,7 +370,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           advance();
           mma_s(0, kslot);
         }
-        umma_commit(&s_full[0]);
+        commit(&s_full[0]);
         ATT_TR(0, 2);
         // ---- tile B
         mbar_wait_ns(&p_half[2], pph, p.peer_timeout_ns);
@@ -331,10 +383,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         release_slot(vslot);
         if (more) {
           mma_s(1, kslot);
-          umma_commit(&s_full[1]);
+          commit(&s_full[1]);
           release_slot(kslot);
         } else {
-          umma_commit(&s_full[1]);
+          commit(&s_full[1]);
         }
         pph ^= 1;
         ATT_TR(0, 4);
@@ -387,8 +439,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (!p.p_halves) mbar_arrive(&p_half[2 * t]);
-          mbar_arrive(&p_half[2 * t + hh]);
+          if constexpr (k2Cta) {  // the leader's MMA thread waits for the P columns of both CTAs
+            if (!p.p_halves) mbar_arrive_leader(&p_half[2 * t]);
+            mbar_arrive_leader(&p_half[2 * t + hh]);
+          } else {
+            if (!p.p_halves) mbar_arrive(&p_half[2 * t]);
+            mbar_arrive(&p_half[2 * t + hh]);
+          }
         }
       }
     };
@@ -573,7 +630,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
   if constexpr (kCluster) cluster_sync_all();  // no arrive / multicast may target a CTA that has already exited
   if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (k2Cta) tmem_dealloc_2sm(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -614,15 +672,15 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
   }
   // G3C_ATTN_MODE: softmax variant (see k_attn_fwd), 2 = sum-guarded reference (default), 0 = exact max per tile;
   // G3C_ATTN_POLY=4: every 4th exponential on the FMA pipe (measured slower, kept for A/B runs)
-  static int poly = -1, mode = 2, cluster = 1;
+  static int poly = -1, mode = 2, cluster = 1, two_cta = 1;
   if (poly < 0) {
     const char* e = getenv("G3C_ATTN_POLY");
     poly = e ? atoi(e) : G3C_ATTN_POLY_DEFAULT;
-    if (poly != 0 && poly != 2 && poly != 3 && poly != 4 && poly != 6) poly = 4;
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<2, 0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<3, 0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    if (poly != 0) poly = 4;  // profiles/r02_attention_variants.txt: 1/6 .. 1/2 all measured slower; 1/4 kept for A/B
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<4, 0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<6, 0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 0, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    e = getenv("G3C_ATTN_2CTA");
+    two_cta = e ? atoi(e) != 0 : 1;
     e = getenv("G3C_ATTN_MODE");
     mode = e ? (atoi(e) != 0 ? 2 : 0) : 2;
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
@@ -668,10 +726,10 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     // also the choice for short key ranges (cross-attention: 4 KV tiles): the CTA is prologue-bound there and the
     // cluster launch / second-pass agreement of the default path only add latency (0.72 vs 0.83 ms at 56 320 x 512)
     k_attn_fwd<0, 0, 0, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
-  } else if (cluster && (grid.x % 2 == 0 || grid.x < 16)) {
-    // CTA pairs along the query dimension sharing every K / V tile through TMA multicast.  An odd number of query
-    // blocks would need a padding CTA (zero-filled Q rows, stores nothing): worth it only for small grids, where it
-    // keeps this path covered by the unit tests; e.g. 55 blocks at cp = 4 run unpaired instead.
+  } else if (cluster && (grid.x % 2 == 0 || grid.x < 16 || (two_cta && !poly))) {
+    // CTA pairs along the query dimension.  An odd number of query blocks gets a padding CTA (zero-filled Q rows,
+    // stores nothing): 1 / grid.x extra work (1.8 % for the 55 blocks of cp = 4) buys the 2-CTA MMAs; the multicast-only
+    // variant pads small grids only (there it keeps the path covered by the unit tests).
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((grid.x + 1) & ~1u, grid.y);
     cfg.blockDim = dim3(ATT_THREADS);
@@ -684,12 +742,29 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    switch (poly) {  // fraction of the exponentials on the FMA pipe: 1/2, 1/3, 1/4, 1/6 of the pairs, or none
-      case 2: G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<2, 0, 2, true>, tmQ, tmK, tmV, p)); break;
-      case 3: G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<3, 0, 2, true>, tmQ, tmK, tmV, p)); break;
-      case 4: G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<4, 0, 2, true>, tmQ, tmK, tmV, p)); break;
-      case 6: G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<6, 0, 2, true>, tmQ, tmK, tmV, p)); break;
-      default: G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 0, 2, true>, tmQ, tmK, tmV, p));
+    if (poly) {  // G3C_ATTN_POLY: a quarter of the exponential pairs on the FMA pipe (measured slower)
+      G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<4, 0, 2, true>, tmQ, tmK, tmV, p));
+    } else if (two_cta) {
+      // default: one 256-row UMMA per tile for the CTA pair; each CTA stages 64 keys of a K tile / 64 head dimensions
+      // of a V^T tile (TMA boxes of 64 rows)
+      CUtensorMap tmK2, tmV2;
+      {
+        uint64_t dims[2] = {(uint64_t)heads * 128, (uint64_t)Lk}, str[1] = {(uint64_t)ldk * 2};
+        uint32_t box[2] = {64, 64};
+        int rc = make_tmap_bf16_sw128(&tmK2, k, 2, dims, str, box);
+        if (rc) return rc;
+      }
+      {
+        const int chunks = Lk / vt_chunk_len;
+        uint64_t dims[3] = {(uint64_t)vt_chunk_len, (uint64_t)heads * 128, (uint64_t)chunks};
+        uint64_t str[2] = {(uint64_t)vt_chunk_len * 2, (uint64_t)vt_chunk_len * 2 * heads * 128};
+        uint32_t box[3] = {64, 64, 1};
+        int rc = make_tmap_bf16_sw128(&tmV2, vt, 3, dims, str, box);
+        if (rc) return rc;
+      }
+      G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 0, 2, true, true>, tmQ, tmK2, tmV2, p));
+    } else {
+      G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 0, 2, true>, tmQ, tmK, tmV, p));
     }
   } else if (poly) {
     k_attn_fwd<4, 0, 2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);

@@ -126,6 +126,48 @@ __global__ void __launch_bounds__(256) k_project_max(const float* __restrict__ p
   block_atomic_max(m, gmax + item / group);
 }
 
+// Broadcast cache frame (src_frames == 1: every target camera of a batch element renders the same N source frames): all
+// F cameras in ONE pass over the points.  A thread keeps 4 points in registers and evaluates the projected depth for
+// camera after camera (uniform loads of the 21 camera floats); per camera: warp max -> shared-memory atomicMax, at the
+// end one global atomicMax per camera and block.  The separate per-item pass above re-read the 10.8 MB point cloud once
+// per target frame (121 x): 372 us -> ~20 us for the 121-frame render.
+constexpr int PM_MAX_CAM = 512;
+__global__ void __launch_bounds__(256)
+    k_project_max_bcast(const float* __restrict__ points, const float* __restrict__ w2c, const float* __restrict__ K,
+                        int N, int F, int HW, int group, float* gmax) {
+  __shared__ float smax[PM_MAX_CAM];
+  const int srcidx = blockIdx.y;           // (b, n)
+  const int b = srcidx / N, n = srcidx - b * N;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) smax[f] = 0.0f;
+  __syncthreads();
+  const float* p = points + (size_t)srcidx * HW * 3;
+  float px[4], py[4], pz[4];
+  int cnt = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW && cnt < 4; i += gridDim.x * blockDim.x, ++cnt) {
+    px[cnt] = p[3 * i]; py[cnt] = p[3 * i + 1]; pz[cnt] = p[3 * i + 2];
+  }
+  for (int f = 0; f < F; ++f) {
+    const int cam = b * F + f;
+    const Cam c = load_cam(w2c + 16 * cam, K + 9 * cam);
+    float m = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < cnt) {
+        float qx, qy, qz;
+        project(c, px[j], py[j], pz[j], qx, qy, qz);
+        const float lz = log_depth(qz);
+        m = (lz > m || lz != lz) ? lz : m;  // propagate NaN like torch.max
+      }
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(&smax[f]), __float_as_int(m));
+  }
+  __syncthreads();
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    const int item = (b * F + f) * N + n;
+    atomicMax(reinterpret_cast<int*>(gmax + item / group), __float_as_int(smax[f]));
+  }
+}
+
 __global__ void __launch_bounds__(256) k_depth_max(const float* __restrict__ depth, size_t n,
                                                   float* gmax) {
   float m = 0.0f;
@@ -840,9 +882,15 @@ static int render_items(g3c_render* r, const float* points, const float* image, 
               r->gmax_cap);
   G3C_REQUIRE(C >= 1 && C <= 3, "render: C=%d unsupported (1..3)", C);
   G3C_CUDA(cudaMemsetAsync(r->gmax, 0, sizeof(float) * n_groups, st));
-  for (int i0 = 0; i0 < n_items; i0 += 65535) {
-    int n = n_items - i0 < 65535 ? n_items - i0 : 65535;
-    k_project_max<<<px_grid(HW, n), 256, 0, st>>>(points, w2c, K, map, i0, HW, group, r->gmax);
+  if (map.src_bcast && map.F <= PM_MAX_CAM && n_items / map.F <= 65535) {
+    // every pixel exactly once: 4 pixels per thread, no grid-stride remainder beyond that
+    const int bx = (HW + 4 * 256 - 1) / (4 * 256);
+    k_project_max_bcast<<<dim3(bx, n_items / map.F), 256, 0, st>>>(points, w2c, K, map.N, map.F, HW, group, r->gmax);
+  } else {
+    for (int i0 = 0; i0 < n_items; i0 += 65535) {
+      int n = n_items - i0 < 65535 ? n_items - i0 : 65535;
+      k_project_max<<<px_grid(HW, n), 256, 0, st>>>(points, w2c, K, map, i0, HW, group, r->gmax);
+    }
   }
   size_t plane = (size_t)(H + 2) * (W + 2);
   for (int i0 = 0; i0 < n_items; i0 += r->max_items) {

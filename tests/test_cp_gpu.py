@@ -69,3 +69,60 @@ def test_context_parallel_cp2_matches_oracle(mode):
     rel = float((got - want).norm() / want.norm())
     print(f"cp2 [{mode}] rel-L2 vs oracle", rel)
     assert rel < 5e-3
+
+
+def _hybrid_worker(rank, world, port, layout, ret):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import bench
+
+        cfg_size = 2 if layout == "cfgxcp" else 1
+        cp_size = world // cfg_size
+        cfg_role, cp_rank = rank // cp_size, rank % cp_size
+        cp_groups = [dist.new_group(list(range(c * cp_size, (c + 1) * cp_size))) for c in range(cfg_size)]
+        pair_groups = [dist.new_group([i, i + cp_size]) for i in range(cp_size)] if cfg_size == 2 else []
+
+        def setup(n):
+            if cp_size > 1:
+                n.enable_context_parallel(cp_groups[cfg_role])
+            if cfg_size == 2:
+                n.enable_cfg_parallel(pair_groups[cp_rank])
+
+        res = bench.sharded_step_parity(torch, dist, dev, setup, cp_size, cp_rank)
+        if rank == 0:
+            ret.put(res)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("layout", ["cfgxcp", "cp"])
+def test_sharded_denoise_step_matches_unsharded(layout):
+    """The gate bench.py runs before timing anything on N > 1 GPUs, as a test: one denoise step of a tiny net sharded
+    (a) CFG-parallel (cond forward on rank 0, uncond on rank 1, outputs swapped through peer memory; with 4+ GPUs also
+    context parallel inside each half) or (b) context-parallel over all ranks, against the unsharded step on every rank."""
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    world = 4 if n >= 4 else 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 29800 + (os.getpid() % 1000) + (11 if layout == "cp" else 0)
+    procs = [ctx.Process(target=_hybrid_worker, args=(r, world, port, layout, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = ret.get(timeout=400)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    print(layout, res)
+    assert res["net_output_rel_l2_max_over_ranks"] < res["tol"] and res["x_next_rel_l2_max_over_ranks"] < 1e-3

@@ -7,15 +7,17 @@ sys.path.insert(0, ".")
 from gen3c_b200 import _lib, ops  # noqa: E402
 
 L, H = 56320, 32
-q = (torch.randn(L, H * 128, device="cuda")).to(torch.bfloat16)
+# the engine's calling convention: softmax scale * log2(e) folded into Q, scale = ln 2 (reference-free fast tiles)
+q = (torch.randn(L, H * 128, device="cuda") * (128 ** -0.5 * 1.4426950408889634)).to(torch.bfloat16)
+LN2 = 0.6931471805599453
 k = (torch.randn(L, H * 128, device="cuda")).to(torch.bfloat16)
 vt = (torch.randn(H * 128, L, device="cuda")).to(torch.bfloat16)
-ops.attention(q, k, vt, H)
+ops.attention(q, k, vt, H, scale=LN2)
 torch.cuda.synchronize()
 buf = torch.zeros(3 * 64 * 8, dtype=torch.int64, device="cuda")
 lib = _lib.load()
 _lib.check(lib.g3c_attn_set_trace(buf.data_ptr()), "set_trace")
-ops.attention(q, k, vt, H)
+ops.attention(q, k, vt, H, scale=LN2)
 torch.cuda.synchronize()
 _lib.check(lib.g3c_attn_set_trace(None), "set_trace")
 t = buf.cpu().view(3, 64, 8).double()

@@ -20,6 +20,29 @@ if which == "attn":
     q, k, vt = bf(L, H * 128, sc=128 ** -0.5 * 1.4426950408889634), bf(L, H * 128), bf(H * 128, L)
     for _ in range(2):
         o = ops.attention(q, k, vt, H, scale=0.6931471805599453)
+elif which == "sdpa":
+    # torch's fused SDPA (cuDNN / flash backend) on the same shape: what the hot kernel is measured against
+    L, H = 56320, 32
+    q, k, v = bf(1, H, L, 128, sc=0.3), bf(1, H, L, 128), bf(1, H, L, 128)
+    for _ in range(2):
+        o = torch.nn.functional.scaled_dot_product_attention(q, k, v)
+elif which == "attn_cp8":
+    L, H = 56320, 32
+    q, k, vt = bf(L // 8, H * 128, sc=128 ** -0.5 * 1.4426950408889634), bf(L, H * 128), bf(H * 128, L)
+    for _ in range(2):
+        o = ops.attention(q, k, vt, H, scale=0.6931471805599453)
+elif which == "eltwise":
+    L, D = 56320, 4096
+    x = torch.randn(L, D, device="cuda")
+    pos = bf(L, D)
+    sh, sc_ = torch.randn(D, device="cuda"), torch.randn(D, device="cuda")
+    for _ in range(2):
+        ops.ln_modulate(x, sh, sc_, pos=pos)
+    a, w = bf(512, 1024), bf(4096, 1024, sc=0.02)           # context K projection (1-CTA kernel)
+    gq = torch.ones(128, device="cuda")
+    for _ in range(2):
+        ops.gemm_norm_rope(a, w, gq)
+        ops.gemm(bf(L, 4096), bf(64, 4096, sc=0.02), ops.EPI_F32, block_n=64)   # final layer
 elif which == "gemm":
     L = 56320
     a, w = bf(L, 4096), bf(4096, 4096, sc=0.02)
