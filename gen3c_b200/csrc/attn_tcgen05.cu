@@ -29,6 +29,7 @@
 // FADD2 row sums.  CTA pairs share every K / V tile through TMA multicast (kCluster).
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 #include "kernels.h"
 
@@ -59,6 +60,7 @@ struct AttnParams {
   unsigned long long* wait_ns;         // optional profiling counter: ns spent polling chunk flags, summed over CTAs
   int unit_scale;             // 1: scale_log2 == 1 (the caller folded softmax scale * log2 e into Q): S is in log2 units
   int p_halves;               // 1: P is released to the MMA warp per 64-key half, 0: per 128-key tile
+  int st_overlap;             // 1: the first P half is released after the first 16 exponentials of the second half
   unsigned long long* trace;  // kTrace only: [3 roles][64 steps][8 slots] clock64 stamps of CTA (0,0)
 };
 
@@ -526,9 +528,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       if (plain) {
         // p = 2^s: one MUFU per element, one FADD2 and one F2FP per pair
         uint64_t ls2[2] = {0ull, 0ull};
-        auto exp64p = [&]() {
+        auto exp_pairs = [&](auto lo, auto hi) {   // pairs [lo, hi) of the 32 pairs of a 64-key half
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = decltype(lo)::value; i < decltype(hi)::value; ++i) {
             float a, b;
             // kPolyEvery = n > 0: every n-th PAIR of exponentials runs on the FMA pipe (packed polynomial)
             if (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == (kPolyEvery > 0 ? kPolyEvery - 1 : 0)) {
@@ -541,14 +543,27 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
             pk[i] = pack_bf16x2(a, b);
           }
         };
-        exp64p();
+        using I0 = std::integral_constant<int, 0>;
+        using I8 = std::integral_constant<int, 8>;
+        using I32 = std::integral_constant<int, 32>;
+        exp_pairs(I0{}, I32{});
         tmem_st32(tS, pk);
-        tmem_ld32(tS + 64, s);  // second half of the row arrives under the release of the first P half
+        tmem_ld32(tS + 64, s);  // second half of the row
         tmem_ld32(tS + 96, s + 32);
-        release_half(0);
-        if (tr) ATT_TR(1 + t, 4);
-        tc_wait_ld();
-        exp64p();
+        if (p.st_overlap) {
+          // the store of the first P half completes under the first 16 exponentials of the second half: its
+          // tcgen05.wait::st (~150 clk when taken right after the store) no longer sits in this warp's critical path
+          tc_wait_ld();
+          exp_pairs(I0{}, I8{});
+          release_half(0);
+          if (tr) ATT_TR(1 + t, 4);
+          exp_pairs(I8{}, I32{});
+        } else {
+          release_half(0);
+          if (tr) ATT_TR(1 + t, 4);
+          tc_wait_ld();
+          exp_pairs(I0{}, I32{});
+        }
         tmem_st32(tS + 32, pk);
         release_half(1);
         float s0, s1, s2, s3;
@@ -715,6 +730,12 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     halves = e ? (atoi(e) != 0) : 1;
   }
   p.p_halves = halves;
+  static int stovl = -1;
+  if (stovl < 0) {
+    const char* e = getenv("G3C_ATTN_STOVL");
+    stovl = e ? (atoi(e) != 0) : 1;
+  }
+  p.st_overlap = stovl;
   G3C_REQUIRE(p.first_chunk >= 0 && p.first_chunk < Lk / vt_chunk_len, "attn: first chunk %d out of range", p.first_chunk);
   p.trace = g_attn_trace;
   if (g_attn_trace) {
