@@ -61,6 +61,9 @@ struct AttnParams {
   int unit_scale;             // 1: scale_log2 == 1 (the caller folded softmax scale * log2 e into Q): S is in log2 units
   int p_halves;               // 1: P is released to the MMA warp per 64-key half, 0: per 128-key tile
   int st_overlap;             // 1: the first P half is released after the first 16 exponentials of the second half
+  int split_s;                // 2-CTA kernel: S = Q K^T as two 64-key UMMAs; the upper one is issued for step j+1 as soon as
+                              // the softmax has read columns 64..127 of S(j) (they do not alias P), i.e. under the
+                              // exponentials and before P.V(j), which shortens the per-tile dependent chain by half an S MMA
   unsigned long long* trace;  // kTrace only: [3 roles][64 steps][8 slots] clock64 stamps of CTA (0,0)
 };
 
@@ -166,7 +169,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
   uint64_t* kv_empty = bars + 1 + kSlots;         // [slots]
   uint64_t* s_full = bars + 1 + 2 * kSlots;       // [2]
   uint64_t* p_half = bars + 3 + 2 * kSlots;       // [tile][key half]: P columns of 64 keys stored
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7 + 2 * kSlots);
+  uint64_t* hi_free = bars + 7 + 2 * kSlots;      // [tile]: S columns 64..127 have been read (split_s)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9 + 2 * kSlots);
   uint32_t* redo_flag = tmem_ptr + 1;  // kMode 2: some row sum left the fp32 range, repeat in the exact mode
 
   const uint32_t warp = warp_id();
@@ -190,6 +194,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       mbar_init(&s_full[i], 1);
       mbar_init(&p_half[2 * i], k2Cta ? 8 : 4);      // one elected arrive per softmax warp (of both CTAs)
       mbar_init(&p_half[2 * i + 1], k2Cta ? 8 : 4);
+      mbar_init(&hi_free[i], k2Cta ? 8 : 4);
     }
     *redo_flag = 0u;
     fence_barrier_init();
@@ -261,10 +266,21 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           // this CTA's 64 keys of the tile (box 64 x 64, both 64-dim halves); bytes credited to the leader's barrier
           if (crank == 0) mbar_expect_tx(&kv_full[slot], 2 * kSlotBytes);
           else mbar_arrive_leader(&kv_full[slot]);
+          if (p.split_s) {
+            // rows 0..31 of this CTA's part = keys 32*rank.. of the lower 64 keys, rows 32..63 = of the upper 64:
+            // each 64-key UMMA (32 B rows per CTA) then covers a contiguous key range (TMA box 64 x 32)
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-            tma_load_2d_2sm(smem_kv + slot * kSlotBytes + h * kKvHalf, &tmK, &kv_full[slot], head * 128 + h * 64,
-                            kv0 + (int)crank * 64);
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int u = 0; u < 2; ++u)
+                tma_load_2d_2sm(smem_kv + slot * kSlotBytes + h * kKvHalf + u * (kKvHalf / 2), &tmK, &kv_full[slot],
+                                head * 128 + h * 64, kv0 + u * 64 + (int)crank * 32);
+          } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              tma_load_2d_2sm(smem_kv + slot * kSlotBytes + h * kKvHalf, &tmK, &kv_full[slot], head * 128 + h * 64,
+                              kv0 + (int)crank * 64);
+          }
         } else if constexpr (kCluster) {
           mbar_expect_tx(&kv_full[slot], ATT_TILE_BYTES);
           tma_load_2d_mc(smem_kv + slot * ATT_TILE_BYTES + crank * ATT_HALF_BYTES, &tmK, &kv_full[slot],
@@ -329,6 +345,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           else umma_ss(tS[t], sdesc_advance(da, off), sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
         }
       };
+      // split_s (2-CTA only): the 64 keys [64u, 64u+64) of the tile -> S columns [64u, 64u+64); B rows 32u..32u+31 of
+      // this CTA's K part (and of the peer's)
+      auto mma_s_part = [&](int t, uint32_t kslot, int u) {
+        constexpr uint32_t idesc64 = make_idesc_bf16(256, 64);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t half = k >> 2, off = (k & 3) * 32;
+          uint64_t da = make_sdesc_sw128(smem_u32(smem_q + t * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
+          uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + kslot * kSlotBytes + half * kKvHalf + u * (kKvHalf / 2)));
+          umma_ss_2sm(tS[t] + u * 64, sdesc_advance(da, off), sdesc_advance(db, off), idesc64, k != 0 ? 1u : 0u);
+        }
+      };
       auto mma_pv = [&](int t, uint32_t vslot, bool first, int hh) {
         // O_t += P_t V for the 64 keys of half hh: 4 k-steps; A = P from TMEM (bf16 pairs per column)
 #pragma unroll
@@ -345,9 +373,20 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       tc_fence_after();
       uint32_t kslot = slot;
       advance();
-      mma_s(0, kslot);
-      commit(&s_full[0]);
-      mma_s(1, kslot);
+      const bool split = k2Cta && p.split_s;
+      if (split) {
+        if constexpr (k2Cta) {
+          mma_s_part(0, kslot, 0);
+          mma_s_part(0, kslot, 1);
+          commit(&s_full[0]);
+          mma_s_part(1, kslot, 0);
+          mma_s_part(1, kslot, 1);
+        }
+      } else {
+        mma_s(0, kslot);
+        commit(&s_full[0]);
+        mma_s(1, kslot);
+      }
       commit(&s_full[1]);
       release_slot(kslot);
       for (int j = 0; j < n_kv; ++j) {
@@ -362,15 +401,29 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         ATT_TR(0, 1);
         tc_fence_after();
         mma_pv(0, vslot, j == 0, 0);
+        if (split && more) {
+          if constexpr (k2Cta) {
+            mbar_wait_ns(&kv_full[slot], phase, p.peer_timeout_ns);  // K_{j+1}
+            kslot = slot;
+            advance();
+            mbar_wait_ns(&hi_free[0], pph, p.peer_timeout_ns);       // columns 64..127 of S_A(j) are in registers
+            tc_fence_after();
+            mma_s_part(0, kslot, 1);
+          }
+        }
         mbar_wait_ns(&p_half[1], pph, p.peer_timeout_ns);
         tc_fence_after();
         mma_pv(0, vslot, j == 0, 1);
         if (more) {
-          mbar_wait_ns(&kv_full[slot], phase, p.peer_timeout_ns);  // K_{j+1}
-          tc_fence_after();
-          kslot = slot;
-          advance();
-          mma_s(0, kslot);
+          if (split) {
+            if constexpr (k2Cta) mma_s_part(0, kslot, 0);
+          } else {
+            mbar_wait_ns(&kv_full[slot], phase, p.peer_timeout_ns);  // K_{j+1}
+            tc_fence_after();
+            kslot = slot;
+            advance();
+            mma_s(0, kslot);
+          }
         }
         commit(&s_full[0]);
         ATT_TR(0, 2);
@@ -379,12 +432,23 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         ATT_TR(0, 3);
         tc_fence_after();
         mma_pv(1, vslot, j == 0, 0);
+        if (split && more) {
+          if constexpr (k2Cta) {
+            mbar_wait_ns(&hi_free[1], pph, p.peer_timeout_ns);
+            tc_fence_after();
+            mma_s_part(1, kslot, 1);
+          }
+        }
         mbar_wait_ns(&p_half[3], pph, p.peer_timeout_ns);
         tc_fence_after();
         mma_pv(1, vslot, j == 0, 1);
         release_slot(vslot);
         if (more) {
-          mma_s(1, kslot);
+          if (split) {
+            if constexpr (k2Cta) mma_s_part(1, kslot, 0);
+          } else {
+            mma_s(1, kslot);
+          }
           commit(&s_full[1]);
           release_slot(kslot);
         } else {
@@ -451,6 +515,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         }
       }
     };
+    // split_s: columns 64..127 of this tile's S are in registers -> the MMA warp may compute S(j+1) of the upper 64 keys
+    // into them (call once per tile, after the tcgen05.wait::ld that covered those columns)
+    auto hi_read = [&]() {
+      if constexpr (k2Cta) {
+        if (p.split_s) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&hi_free[t]);
+        }
+      }
+    };
     auto wait_s = [&](int j) {
       if (tr) ATT_TR(1 + t, 0);
       mbar_wait_ns(&s_full[t], sphase, p.peer_timeout_ns);
@@ -466,6 +541,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) tmem_ld32(tS + cc * 32, s + cc * 32);
       tc_wait_ld();
+      hi_read();
       if (tr) ATT_TR(1 + t, 2);
       // 8 independent max chains (a single dependent FMNMX chain costs ~6 clk per link)
       float mxs[8];
@@ -554,6 +630,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           // the store of the first P half completes under the first 16 exponentials of the second half: its
           // tcgen05.wait::st (~150 clk when taken right after the store) no longer sits in this warp's critical path
           tc_wait_ld();
+          hi_read();
           exp_pairs(I0{}, I8{});
           release_half(0);
           if (tr) ATT_TR(1 + t, 4);
@@ -562,6 +639,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           release_half(0);
           if (tr) ATT_TR(1 + t, 4);
           tc_wait_ld();
+          hi_read();
           exp_pairs(I0{}, I32{});
         }
         tmem_st32(tS + 32, pk);
@@ -580,6 +658,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         release_half(0);
         if (tr) ATT_TR(1 + t, 4);
         tc_wait_ld();
+        hi_read();
         exp64(s, neg, pk, ls);
         tmem_st32(tS + 32, pk);
         release_half(1);
@@ -736,6 +815,12 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     stovl = e ? (atoi(e) != 0) : 1;
   }
   p.st_overlap = stovl;
+  static int splits = -1;
+  if (splits < 0) {
+    const char* e = getenv("G3C_ATTN_SPLITS");
+    splits = e ? (atoi(e) != 0) : 1;
+  }
+  p.split_s = splits;
   G3C_REQUIRE(p.first_chunk >= 0 && p.first_chunk < Lk / vt_chunk_len, "attn: first chunk %d out of range", p.first_chunk);
   p.trace = g_attn_trace;
   if (g_attn_trace) {
@@ -771,7 +856,7 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
       CUtensorMap tmK2, tmV2;
       {
         uint64_t dims[2] = {(uint64_t)heads * 128, (uint64_t)Lk}, str[1] = {(uint64_t)ldk * 2};
-        uint32_t box[2] = {64, 64};
+        uint32_t box[2] = {64, p.split_s ? 32u : 64u};   // split_s: two 32-key boxes per 64-dim half (see the loader)
         int rc = make_tmap_bf16_sw128(&tmK2, k, 2, dims, str, box);
         if (rc) return rc;
       }
