@@ -319,20 +319,31 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       }
     }
   } else if (warp == 9) {
-    if (lane == 0 && (!k2Cta || crank == 0)) {
-      // ===== MMA issuer (2-CTA: one thread of the leader issues for both SMs) =====
+    if (!k2Cta || crank == 0) {
+      // ===== MMA issuer (2-CTA: the leader issues for both SMs) =====
+      // The WHOLE warp runs this control flow converged and one elected lane issues the tcgen05 instructions.  With
+      // the loop inside `if (lane == 0)` every operand (descriptors, TMEM addresses) was lane-divergent for ptxas: 5
+      // R2UR + an ELECT/broadcast loop between consecutive UTCHMMA (11 SASS instructions, ~86 clk per MMA measured with
+      // clock64 — more than the 68 clk the 128x128x16 MMA needs), i.e. the tensor pipe was fed by an issue-bound
+      // thread.  Warp-uniform values live in uniform registers and the UTCHMMAs go out back to back.
+      const bool issuer = elect_one();
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);   // tells the compiler the address is uniform
       constexpr uint32_t idesc = make_idesc_bf16(k2Cta ? 256 : 128, 128);
-      const uint32_t tS[2] = {tmem_base, tmem_base + 128};
-      const uint32_t tO[2] = {tmem_base + 256, tmem_base + 384};
+      const uint32_t tS[2] = {tbase, tbase + 128};
+      const uint32_t tO[2] = {tbase + 256, tbase + 384};
       auto advance = [&]() { if (++slot == kSlots) { slot = 0; phase ^= 1; } };
       auto commit = [&](uint64_t* bar) {   // s_full: seen by the softmax warps of every CTA the MMAs wrote to
-        if constexpr (k2Cta) umma_commit_2sm(bar);
-        else umma_commit(bar);
+        if (issuer) {
+          if constexpr (k2Cta) umma_commit_2sm(bar);
+          else umma_commit(bar);
+        }
       };
       auto release_slot = [&](uint32_t sl) {
-        if constexpr (k2Cta) umma_commit_2sm(&kv_empty[sl]);
-        else if constexpr (kCluster) umma_commit_mc(&kv_empty[sl], 3);
-        else umma_commit(&kv_empty[sl]);
+        if (issuer) {
+          if constexpr (k2Cta) umma_commit_2sm(&kv_empty[sl]);
+          else if constexpr (kCluster) umma_commit_mc(&kv_empty[sl], 3);
+          else umma_commit(&kv_empty[sl]);
+        }
       };
       auto mma_s = [&](int t, uint32_t kslot) {
         // S_t = Q_t K^T : 8 k-steps over the head dimension
@@ -341,8 +352,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           const uint32_t half = k >> 2, off = (k & 3) * 32;
           uint64_t da = make_sdesc_sw128(smem_u32(smem_q + t * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
           uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + kslot * kSlotBytes + half * kKvHalf));
-          if constexpr (k2Cta) umma_ss_2sm(tS[t], sdesc_advance(da, off), sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
-          else umma_ss(tS[t], sdesc_advance(da, off), sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
+          if (issuer) {
+            if constexpr (k2Cta) umma_ss_2sm(tS[t], sdesc_advance(da, off), sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
+            else umma_ss(tS[t], sdesc_advance(da, off), sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
+          }
         }
       };
       // split_s (2-CTA only): the 64 keys [64u, 64u+64) of the tile -> S columns [64u, 64u+64); B rows 32u..32u+31 of
@@ -354,7 +367,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           const uint32_t half = k >> 2, off = (k & 3) * 32;
           uint64_t da = make_sdesc_sw128(smem_u32(smem_q + t * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
           uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + kslot * kSlotBytes + half * kKvHalf + u * (kKvHalf / 2)));
-          umma_ss_2sm(tS[t] + u * 64, sdesc_advance(da, off), sdesc_advance(db, off), idesc64, k != 0 ? 1u : 0u);
+          if (issuer) umma_ss_2sm(tS[t] + u * 64, sdesc_advance(da, off), sdesc_advance(db, off), idesc64, k != 0 ? 1u : 0u);
         }
       };
       auto mma_pv = [&](int t, uint32_t vslot, bool first, int hh) {
@@ -364,8 +377,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           const int k = hh * 4 + kk;
           const uint32_t half = k >> 2, off = (k & 3) * 32;
           uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + vslot * kSlotBytes + half * kKvHalf));
-          if constexpr (k2Cta) umma_ts_2sm(tO[t], tS[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
-          else umma_ts(tO[t], tS[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
+          if (issuer) {
+            if constexpr (k2Cta) umma_ts_2sm(tO[t], tS[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
+            else umma_ts(tO[t], tS[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
+          }
         }
       };
       if (pass == 0) mbar_wait_ns(q_full, 0, p.peer_timeout_ns);
@@ -818,7 +833,7 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
   static int splits = -1;
   if (splits < 0) {
     const char* e = getenv("G3C_ATTN_SPLITS");
-    splits = e ? (atoi(e) != 0) : 1;
+    splits = e ? (atoi(e) != 0) : 0;  // measured 977 vs 1 235 TFLOP/s: 64-key UMMAs cost as much as 128-key ones
   }
   p.split_s = splits;
   G3C_REQUIRE(p.first_chunk >= 0 && p.first_chunk < Lk / vt_chunk_len, "attn: first chunk %d out of range", p.first_chunk);

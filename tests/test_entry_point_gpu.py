@@ -126,3 +126,65 @@ def test_checkpoint_round_trip_through_model_pt(tmp_path):
     after, want = fwd(dst.net).float(), fwd(src).float()
     assert float(before.abs().max()) == 0.0 and float(want.abs().max()) > 0
     assert torch.equal(after, want)
+
+
+def _persistent_args(tmp_path):
+    from gen3c_b200.inference import gen3c_persistent as pm
+
+    argv = ["--synthetic", "--prompt", "a room", "--trajectory", "none", "--video_save_name", "", "--disable_guardrail",
+            "--disable_prompt_upsampler", "--disable_prompt_encoder", "--height", "128", "--width", "256", "--num_steps", "2",
+            "--video_save_folder", str(tmp_path / "out"), "--seed", "5"]
+    return pm, pm.create_parser().parse_args(argv)
+
+
+def test_persistent_model_single_image_seed_and_cameras(tmp_path):
+    """Gen3cPersistentModel (server-side caller): seed from one image by value, then serve a 121-camera request with
+    estimated depths returned (reference gen3c_persistent.py:138-515)."""
+    from gen3c_b200.camera_utils import generate_camera_trajectory
+
+    pm, args = _persistent_args(tmp_path)
+    model = pm.Gen3cPersistentModel(args, pipeline=_pipeline(args))
+    img = np.random.RandomState(1).rand(1, 90, 160, 3).astype(np.float32)
+    w2c, focal, pp, res = model.seed_model_from_values(img, None, np.eye(4, dtype=np.float32)[None], np.ones((1, 2), np.float32),
+                                                       np.full((1, 2), 0.5, np.float32), np.array([[160, 90]]))
+    assert w2c.shape == (1, 4, 4) and focal.shape == (1, 2) and pp.shape == (1, 2) and list(res[0]) == [256, 128]
+    assert model.seeding_image.shape == (1, 3, 1, 128, 256) and model.model_was_seeded
+    K = np.array([[focal[0, 0], 0, pp[0, 0]], [0, focal[0, 1], pp[0, 1]], [0, 0, 1]], dtype=np.float32)
+    w2cs, Ks = generate_camera_trajectory("right", torch.eye(4), torch.from_numpy(K), 121, 0.2, "center_facing", device="cpu")
+    out = model.inference_on_cameras(w2cs[0].numpy(), Ks[0].numpy(), fps=24, return_estimated_depths=True)
+    assert out["video"].shape == (1, 121, 3, 128, 256) and out["video"].dtype == np.uint8
+    assert out["rendered_warp_images"].shape == (1, 121, 1, 3, 128, 256)
+    d = out["predicted_depth"]
+    assert d.shape == (121, 1, 128, 256) and np.isnan(d[:-1]).all() and np.isfinite(d[-1]).all()
+    assert model.get_cache_input_depths().shape == (1, 1, 128, 256)
+    model.clear_cache()
+    assert model.cache is None and not model.model_was_seeded
+    with pytest.raises(AssertionError):   # persistent mode takes images by value
+        bad = pm.create_parser().parse_args(["--prompt", "x", "--trajectory", "none", "--video_save_name", "",
+                                             "--input_image_path", "a.png"])
+        pm.validate_args(bad)
+
+
+def test_persistent_model_multiframe_seed_uses_cache4d(tmp_path):
+    from gen3c_b200.cache_3d import Cache4D
+
+    pm, args = _persistent_args(tmp_path)
+    model = pm.Gen3cPersistentModel(args, pipeline=_pipeline(args))
+    n, h, w = 121, 128, 256
+    rs = np.random.RandomState(2)
+    imgs = rs.rand(n, h, w, 3).astype(np.float32)
+    depths = (2.0 + rs.rand(n, h, w)).astype(np.float32)
+    masks = np.ones((n, h, w), np.float32)
+    w2cs = np.tile(np.eye(4, dtype=np.float32)[None], (n, 1, 1))
+    w2cs[:, 0, 3] = np.linspace(0, 0.1, n)
+    focal = np.full((n, 2), 220.0, np.float32)
+    pp = np.full((n, 2), 0.5, np.float32)
+    model.seed_model_from_values(imgs, depths, w2cs, focal, pp, np.tile([[w, h]], (n, 1)), masks)
+    assert isinstance(model.cache, Cache4D) and model.cache.input_frame_count() == n
+    K = np.zeros((n, 3, 3), np.float32)
+    K[:, 0, 0] = K[:, 1, 1] = 220.0
+    K[:, 0, 2], K[:, 1, 2], K[:, 2, 2] = 0.5 * w, 0.5 * h, 1.0
+    out = model.inference_on_cameras(w2cs, K, fps=24)
+    assert out["video"].shape == (1, n, 3, h, w) and out["predicted_depth"] is None
+    with pytest.raises(NotImplementedError):
+        model.seed_model_from_values(imgs[:2], None, w2cs[:2], focal[:2], pp[:2], np.tile([[w, h]], (2, 1)))
