@@ -294,14 +294,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer (single thread) =====
+    {
+      // ===== MMA issuer: the warp runs converged, one elected lane issues (operands stay in uniform registers; inside
+      // `if (lane == 0)` ptxas put 5 R2UR + a broadcast loop between consecutive UTCHMMAs — see attn_tcgen05.cu) =====
+      const bool issuer = elect_one();
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN;
+        const uint32_t d_tmem = tbase + as * BN;
         for (int kb = 0; kb < p.num_k_blk; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -309,16 +312,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
           const uint64_t db = make_sdesc_sw128(smem_u32(smem_b + stage * S::kBBytes));
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_ss(d_tmem, sdesc_advance(da, k * UMMA_K * 2), sdesc_advance(db, k * UMMA_K * 2),
-                    idesc, (kb | k) != 0 ? 1u : 0u);
+            if (issuer)
+              umma_ss(d_tmem, sdesc_advance(da, k * UMMA_K * 2), sdesc_advance(db, k * UMMA_K * 2),
+                      idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);
+          if (issuer) umma_commit(&empty[stage]);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull[as]);
+        if (issuer) umma_commit(&tfull[as]);
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -456,14 +460,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ===== MMA issuer (one thread of the leader CTA) =====
+    if (leader) {
+      // ===== MMA issuer (leader CTA; warp converged, one elected lane issues) =====
+      const bool issuer = elect_one();
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
       constexpr uint32_t idesc = make_idesc_bf16(256, BN2);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BN2;
+        const uint32_t d_tmem = tbase + as * BN2;
         for (int kb = 0; kb < p.num_k_blk; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -471,16 +477,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
           const uint64_t db = make_sdesc_sw128(smem_u32(smem_b + stage * S::kBBytes));
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_ss_2sm(d_tmem, sdesc_advance(da, k * UMMA_K * 2), sdesc_advance(db, k * UMMA_K * 2), idesc,
-                        (kb | k) != 0 ? 1u : 0u);
+            if (issuer)
+              umma_ss_2sm(d_tmem, sdesc_advance(da, k * UMMA_K * 2), sdesc_advance(db, k * UMMA_K * 2), idesc,
+                          (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit_2sm(&empty[stage]);
+          if (issuer) umma_commit_2sm(&empty[stage]);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2sm(&tfull[as]);
+        if (issuer) umma_commit_2sm(&tfull[as]);
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
