@@ -61,6 +61,7 @@ struct AttnParams {
   int unit_scale;             // 1: scale_log2 == 1 (the caller folded softmax scale * log2 e into Q): S is in log2 units
   int p_halves;               // 1: P is released to the MMA warp per 64-key half, 0: per 128-key tile
   int st_overlap;             // 1: the first P half is released after the first 16 exponentials of the second half
+  int p_quarters;             // 1: reference-free fast tiles release P in four 32-key quarters (software-pipelined stores)
   int split_s;                // 2-CTA kernel: S = Q K^T as two 64-key UMMAs; the upper one is issued for step j+1 as soon as
                               // the softmax has read columns 64..127 of S(j) (they do not alias P), i.e. under the
                               // exponentials and before P.V(j), which shortens the per-tile dependent chain by half an S MMA
@@ -148,7 +149,7 @@ __device__ __forceinline__ float ex2_poly(float x) {
 //           shared-memory operand traffic of the tensor pipe and the TMA fill per SM are halved against the multicast
 //           variant (whose MMAs ran at ~82 % of their nominal rate: 1 388 clk per PV+S pair instead of 1 134, clock64
 //           timeline in profiles/r02_attn_trace.txt), and the ring holds 8 instead of 4 tiles in the same 128 KB.
-//           The leader's MMA thread issues for both SMs; `kv_full` / `p_half` / `q_full` live in the leader and collect
+//           The leader's MMA thread issues for both SMs; `kv_full` / `p_part` / `q_full` live in the leader and collect
 //           both CTAs' arrivals, `s_full` / `kv_empty` are hit in both CTAs by multicast commits.
 template <int kPolyEvery, int kTrace, int kMode, bool kCluster, bool k2Cta = false>  // kTrace 1: stamps in every role, 2: MMA warp only
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -168,9 +169,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
   uint64_t* kv_full = bars + 1;                   // [slots]
   uint64_t* kv_empty = bars + 1 + kSlots;         // [slots]
   uint64_t* s_full = bars + 1 + 2 * kSlots;       // [2]
-  uint64_t* p_half = bars + 3 + 2 * kSlots;       // [tile][key half]: P columns of 64 keys stored
-  uint64_t* hi_free = bars + 7 + 2 * kSlots;      // [tile]: S columns 64..127 have been read (split_s)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9 + 2 * kSlots);
+  uint64_t* p_part = bars + 3 + 2 * kSlots;       // [tile][key quarter]: P columns of 32 keys stored
+  uint64_t* hi_free = bars + 11 + 2 * kSlots;     // [tile]: S columns 64..127 have been read (split_s)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13 + 2 * kSlots);
   uint32_t* redo_flag = tmem_ptr + 1;  // kMode 2: some row sum left the fp32 range, repeat in the exact mode
 
   const uint32_t warp = warp_id();
@@ -192,8 +193,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_half[2 * i], k2Cta ? 8 : 4);      // one elected arrive per softmax warp (of both CTAs)
-      mbar_init(&p_half[2 * i + 1], k2Cta ? 8 : 4);
+      for (int q = 0; q < 4; ++q) mbar_init(&p_part[4 * i + q], k2Cta ? 8 : 4);  // one elected arrive per softmax warp (of both CTAs)
       mbar_init(&hi_free[i], k2Cta ? 8 : 4);
     }
     *redo_flag = 0u;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 
   // Pipeline state of every role lives outside the pass loop: kMode 2 may run the KV sweep a second time.
   uint32_t slot = 0, phase = 0;  // KV ring position (TMA warp: producer side, MMA warp: consumer side)
-  uint32_t pph = 0;              // MMA warp: parity of the p_half barriers
+  uint32_t pph = 0;              // MMA warp: parity of the p_part barriers
   uint32_t sphase = 0;           // softmax warps: parity of s_full
   int pass = 0;
   for (;;) {
@@ -370,11 +370,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           if (issuer) umma_ss_2sm(tS[t] + u * 64, sdesc_advance(da, off), sdesc_advance(db, off), idesc64, k != 0 ? 1u : 0u);
         }
       };
-      auto mma_pv = [&](int t, uint32_t vslot, bool first, int hh) {
-        // O_t += P_t V for the 64 keys of half hh: 4 k-steps; A = P from TMEM (bf16 pairs per column)
+      auto mma_pv = [&](int t, uint32_t vslot, bool first, int qq) {
+        // O_t += P_t V for the 32 keys of quarter qq: 2 k-steps; A = P from TMEM (bf16 pairs per column)
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const int k = hh * 4 + kk;
+        for (int kk = 0; kk < 2; ++kk) {
+          const int k = qq * 2 + kk;
           const uint32_t half = k >> 2, off = (k & 3) * 32;
           uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + vslot * kSlotBytes + half * kKvHalf));
           if (issuer) {
@@ -412,10 +412,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         // ---- tile A
         ATT_TR(0, 0);
         // the P·V MMAs of the first 64 keys start while the softmax still exponentiates the second 64
-        mbar_wait_ns(&p_half[0], pph, p.peer_timeout_ns);
+        mbar_wait_ns(&p_part[0], pph, p.peer_timeout_ns);
         ATT_TR(0, 1);
         tc_fence_after();
         mma_pv(0, vslot, j == 0, 0);
+        mbar_wait_ns(&p_part[1], pph, p.peer_timeout_ns);
+        tc_fence_after();
+        mma_pv(0, vslot, j == 0, 1);
         if (split && more) {
           if constexpr (k2Cta) {
             mbar_wait_ns(&kv_full[slot], phase, p.peer_timeout_ns);  // K_{j+1}
@@ -426,9 +429,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
             mma_s_part(0, kslot, 1);
           }
         }
-        mbar_wait_ns(&p_half[1], pph, p.peer_timeout_ns);
+        mbar_wait_ns(&p_part[2], pph, p.peer_timeout_ns);
         tc_fence_after();
-        mma_pv(0, vslot, j == 0, 1);
+        mma_pv(0, vslot, j == 0, 2);
+        mbar_wait_ns(&p_part[3], pph, p.peer_timeout_ns);
+        tc_fence_after();
+        mma_pv(0, vslot, j == 0, 3);
         if (more) {
           if (split) {
             if constexpr (k2Cta) mma_s_part(0, kslot, 0);
@@ -443,10 +449,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         commit(&s_full[0]);
         ATT_TR(0, 2);
         // ---- tile B
-        mbar_wait_ns(&p_half[2], pph, p.peer_timeout_ns);
+        mbar_wait_ns(&p_part[4], pph, p.peer_timeout_ns);
         ATT_TR(0, 3);
         tc_fence_after();
         mma_pv(1, vslot, j == 0, 0);
+        mbar_wait_ns(&p_part[5], pph, p.peer_timeout_ns);
+        tc_fence_after();
+        mma_pv(1, vslot, j == 0, 1);
         if (split && more) {
           if constexpr (k2Cta) {
             mbar_wait_ns(&hi_free[1], pph, p.peer_timeout_ns);
@@ -454,9 +463,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
             mma_s_part(1, kslot, 1);
           }
         }
-        mbar_wait_ns(&p_half[3], pph, p.peer_timeout_ns);
+        mbar_wait_ns(&p_part[6], pph, p.peer_timeout_ns);
         tc_fence_after();
-        mma_pv(1, vslot, j == 0, 1);
+        mma_pv(1, vslot, j == 0, 2);
+        mbar_wait_ns(&p_part[7], pph, p.peer_timeout_ns);
+        tc_fence_after();
+        mma_pv(1, vslot, j == 0, 3);
         release_slot(vslot);
         if (more) {
           if (split) {
@@ -520,14 +532,23 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if constexpr (k2Cta) {  // the leader's MMA thread waits for the P columns of both CTAs
-            if (!p.p_halves) mbar_arrive_leader(&p_half[2 * t]);
-            mbar_arrive_leader(&p_half[2 * t + hh]);
-          } else {
-            if (!p.p_halves) mbar_arrive(&p_half[2 * t]);
-            mbar_arrive(&p_half[2 * t + hh]);
+          // half hh = quarters 2hh and 2hh+1 (p_halves == 0: the whole tile at hh == 1)
+          const int q0 = p.p_halves ? 2 * hh : 0;
+          for (int q = q0; q <= 2 * hh + 1; ++q) {
+            if constexpr (k2Cta) mbar_arrive_leader(&p_part[4 * t + q]);  // the leader's MMA thread waits for both CTAs
+            else mbar_arrive(&p_part[4 * t + q]);
           }
         }
+      }
+    };
+    // the 16 P columns of key quarter q are in TMEM: make them visible to the tensor pipe and tell the MMA warp
+    auto release_part = [&](int q) {
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (k2Cta) mbar_arrive_leader(&p_part[4 * t + q]);
+        else mbar_arrive(&p_part[4 * t + q]);
       }
     };
     // split_s: columns 64..127 of this tile's S are in registers -> the MMA warp may compute S(j+1) of the upper 64 keys
@@ -636,7 +657,39 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         };
         using I0 = std::integral_constant<int, 0>;
         using I8 = std::integral_constant<int, 8>;
+        using I16 = std::integral_constant<int, 16>;
+        using I24 = std::integral_constant<int, 24>;
         using I32 = std::integral_constant<int, 32>;
+        if (p.p_quarters) {
+          // P leaves in four 32-key quarters; every store completes under the next quarter's first exponentials, the
+          // second half of S is loaded into the registers the first half has already vacated, and the last release
+          // leaves only two P.V k-steps (instead of four) between the end of the softmax and the next S MMA
+          exp_pairs(I0{}, I16{});
+          tmem_st16(tS, pk);
+          tmem_ld32(tS + 64, s);            // s[0..31] are dead: S columns 64..95
+          exp_pairs(I16{}, I24{});
+          release_part(0);
+          if (tr) ATT_TR(1 + t, 4);
+          exp_pairs(I24{}, I32{});
+          tmem_st16(tS + 16, pk + 16);
+          tmem_ld32(tS + 96, s + 32);       // S columns 96..127
+          tc_wait_ld();
+          hi_read();
+          exp_pairs(I0{}, I8{});
+          release_part(1);
+          exp_pairs(I8{}, I16{});
+          tmem_st16(tS + 32, pk);
+          exp_pairs(I16{}, I24{});
+          release_part(2);
+          exp_pairs(I24{}, I32{});
+          tmem_st16(tS + 48, pk + 16);
+          release_part(3);
+          float s0, s1, s2, s3;
+          unpack2(ls2[0], s0, s1);
+          unpack2(ls2[1], s2, s3);
+          fast_tail((s0 + s1) + (s2 + s3), j);
+          return;
+        }
         exp_pairs(I0{}, I32{});
         tmem_st32(tS, pk);
         tmem_ld32(tS + 64, s);  // second half of the row
@@ -788,6 +841,8 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     if (poly != 0) poly = 4;  // profiles/r02_attention_variants.txt: 1/6 .. 1/2 all measured slower; 1/4 kept for A/B
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<4, 0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 0, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 1, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 2, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     e = getenv("G3C_ATTN_2CTA");
     two_cta = e ? atoi(e) != 0 : 1;
     e = getenv("G3C_ATTN_MODE");
@@ -836,9 +891,18 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     splits = e ? (atoi(e) != 0) : 0;  // measured 977 vs 1 235 TFLOP/s: 64-key UMMAs cost as much as 128-key ones
   }
   p.split_s = splits;
+  static int quarters = -1;
+  if (quarters < 0) {
+    const char* e = getenv("G3C_ATTN_PQUARTERS");
+    quarters = e ? (atoi(e) != 0) : 1;
+  }
+  p.p_quarters = quarters && halves;
   G3C_REQUIRE(p.first_chunk >= 0 && p.first_chunk < Lk / vt_chunk_len, "attn: first chunk %d out of range", p.first_chunk);
   p.trace = g_attn_trace;
-  if (g_attn_trace) {
+  const char* tmo = getenv("G3C_ATTN_TRACE_MMA_ONLY");
+  const int trace_level = g_attn_trace ? ((tmo && atoi(tmo)) ? 2 : 1) : 0;
+  const bool trace_2cta = trace_level && mode && two_cta && cluster && !poly && Lk > 8 * ATT_TILE;
+  if (g_attn_trace && !trace_2cta) {
     const char* mo = getenv("G3C_ATTN_TRACE_MMA_ONLY");  // stamps of the MMA warp only: no perturbation of the softmax warps
     if (mode && mo && atoi(mo)) k_attn_fwd<0, 2, 2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
     else if (mode) k_attn_fwd<0, 1, 2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
@@ -883,7 +947,9 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
         int rc = make_tmap_bf16_sw128(&tmV2, vt, 3, dims, str, box);
         if (rc) return rc;
       }
-      G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 0, 2, true, true>, tmQ, tmK2, tmV2, p));
+      if (trace_level == 1) G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 1, 2, true, true>, tmQ, tmK2, tmV2, p));
+      else if (trace_level == 2) G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 2, 2, true, true>, tmQ, tmK2, tmV2, p));
+      else G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 0, 2, true, true>, tmQ, tmK2, tmV2, p));
     } else {
       G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 0, 2, true>, tmQ, tmK, tmV, p));
     }
