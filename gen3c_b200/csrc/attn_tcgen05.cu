@@ -151,11 +151,18 @@ __device__ __forceinline__ float ex2_poly(float x) {
 //           timeline in profiles/r02_attn_trace.txt), and the ring holds 8 instead of 4 tiles in the same 128 KB.
 //           The leader's MMA thread issues for both SMs; `kv_full` / `p_part` / `q_full` live in the leader and collect
 //           both CTAs' arrivals, `s_full` / `kv_empty` are hit in both CTAs by multicast commits.
-template <int kPolyEvery, int kTrace, int kMode, bool kCluster, bool k2Cta = false>  // kTrace 1: stamps in every role, 2: MMA warp only
+// kSharedS: (implies k2Cta) ONE S buffer (128 TMEM columns) shared by both tiles, P in its own 64 columns per tile:
+//           S_t(j+1) no longer waits for P.V_t(j) to drain the P columns that alias S, only for the OTHER tile's softmax
+//           to have pulled its S row into registers.  With MMAs now issued at their native rate (63 clk per 128x128x16,
+//           clock64 trace profiles/r02_attn_trace.txt) the per-tile chain softmax -> P.V -> S -> softmax was the limiter
+//           (tensor pipe 62 % busy, period 3 160-3 260 clk): here the next S is computed while the tile's own softmax
+//           still runs, so the softmax warps run back to back.  TMEM: S [0,128) P_A [128,192) P_B [192,256) O_A O_B.
+template <int kPolyEvery, int kTrace, int kMode, bool kCluster, bool k2Cta = false, bool kSharedS = false>  // kTrace 1: stamps in every role, 2: MMA warp only
 __global__ void __launch_bounds__(ATT_THREADS, 1)
     k_attn_fwd(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   static_assert(!k2Cta || kCluster, "2-CTA MMAs need the cluster launch");
+  static_assert(!kSharedS || k2Cta, "the shared-S variant is built on the 2-CTA kernel");
   constexpr int kSlots = k2Cta ? 2 * ATT_SLOTS : ATT_SLOTS;            // ring entries (one K or V^T tile each)
   constexpr int kSlotBytes = k2Cta ? ATT_TILE_BYTES / 2 : ATT_TILE_BYTES;  // this CTA's part of a tile
   constexpr int kKvHalf = kSlotBytes / 2;                               // one 64-element K-dimension half of it
@@ -171,7 +178,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
   uint64_t* s_full = bars + 1 + 2 * kSlots;       // [2]
   uint64_t* p_part = bars + 3 + 2 * kSlots;       // [tile][key quarter]: P columns of 32 keys stored
   uint64_t* hi_free = bars + 11 + 2 * kSlots;     // [tile]: S columns 64..127 have been read (split_s)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13 + 2 * kSlots);
+  uint64_t* s_free = hi_free;                     // kSharedS: the S buffer has been read into registers (either tile)
+  uint64_t* p_free = bars + 13 + 2 * kSlots;      // kSharedS [tile]: P.V_t(j) has consumed P_t (and updated O_t)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15 + 2 * kSlots);
   uint32_t* redo_flag = tmem_ptr + 1;  // kMode 2: some row sum left the fp32 range, repeat in the exact mode
 
   const uint32_t warp = warp_id();
@@ -195,6 +204,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       mbar_init(&s_full[i], 1);
       for (int q = 0; q < 4; ++q) mbar_init(&p_part[4 * i + q], k2Cta ? 8 : 4);  // one elected arrive per softmax warp (of both CTAs)
       mbar_init(&hi_free[i], k2Cta ? 8 : 4);
+      mbar_init(&p_free[i], 1);
     }
     *redo_flag = 0u;
     fence_barrier_init();
@@ -213,6 +223,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
   // Pipeline state of every role lives outside the pass loop: kMode 2 may run the KV sweep a second time.
   uint32_t slot = 0, phase = 0;  // KV ring position (TMA warp: producer side, MMA warp: consumer side)
   uint32_t pph = 0;              // MMA warp: parity of the p_part barriers
+  uint32_t sfp = 0;              // MMA warp (kSharedS): parity of s_free
   uint32_t sphase = 0;           // softmax warps: parity of s_full
   int pass = 0;
   for (;;) {
@@ -329,7 +340,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       const bool issuer = elect_one();
       const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);   // tells the compiler the address is uniform
       constexpr uint32_t idesc = make_idesc_bf16(k2Cta ? 256 : 128, 128);
-      const uint32_t tS[2] = {tbase, tbase + 128};
+      const uint32_t tS[2] = {tbase, kSharedS ? tbase : tbase + 128};                       // S destination of tile t
+      const uint32_t tPa[2] = {kSharedS ? tbase + 128 : tbase, kSharedS ? tbase + 192 : tbase + 128};  // P (A operand)
       const uint32_t tO[2] = {tbase + 256, tbase + 384};
       auto advance = [&]() { if (++slot == kSlots) { slot = 0; phase ^= 1; } };
       auto commit = [&](uint64_t* bar) {   // s_full: seen by the softmax warps of every CTA the MMAs wrote to
@@ -378,8 +390,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           const uint32_t half = k >> 2, off = (k & 3) * 32;
           uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + vslot * kSlotBytes + half * kKvHalf));
           if (issuer) {
-            if constexpr (k2Cta) umma_ts_2sm(tO[t], tS[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
-            else umma_ts(tO[t], tS[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
+            if constexpr (k2Cta) umma_ts_2sm(tO[t], tPa[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
+            else umma_ts(tO[t], tPa[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
           }
         }
       };
@@ -388,6 +400,64 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       tc_fence_after();
       uint32_t kslot = slot;
       advance();
+      if constexpr (kSharedS) {
+        // every S computation except the very first waits for the previous one (the other tile's) to have been read
+        auto wait_s_free = [&]() {
+          mbar_wait_ns(s_free, sfp, p.peer_timeout_ns);
+          sfp ^= 1;
+          tc_fence_after();
+        };
+        if (pass != 0) wait_s_free();
+        mma_s(0, kslot);
+        commit(&s_full[0]);
+        wait_s_free();
+        mma_s(1, kslot);
+        commit(&s_full[1]);
+        release_slot(kslot);
+        for (int j = 0; j < n_kv; ++j) {
+          const bool more = j + 1 < n_kv;
+          mbar_wait_ns(&kv_full[slot], phase, p.peer_timeout_ns);  // V_j
+          const uint32_t vslot = slot;
+          advance();
+          ATT_TR(0, 0);
+          if (more) {
+            mbar_wait_ns(&kv_full[slot], phase, p.peer_timeout_ns);  // K_{j+1}
+            kslot = slot;
+            advance();
+            wait_s_free();                 // tile B has S_B(j) in registers
+            mma_s(0, kslot);               // S_A(j+1): under the exponentials of softmax A(j)
+            commit(&s_full[0]);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            mbar_wait_ns(&p_part[q], pph, p.peer_timeout_ns);
+            if (q == 0) ATT_TR(0, 1);
+            tc_fence_after();
+            mma_pv(0, vslot, j == 0, q);
+          }
+          commit(&p_free[0]);
+          if (!more) commit(&s_full[0]);   // epilogue: O_A complete
+          ATT_TR(0, 2);
+          if (more) {
+            wait_s_free();                 // tile A has S_A(j+1) in registers
+            mma_s(1, kslot);
+            commit(&s_full[1]);
+            release_slot(kslot);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            mbar_wait_ns(&p_part[4 + q], pph, p.peer_timeout_ns);
+            if (q == 0) ATT_TR(0, 3);
+            tc_fence_after();
+            mma_pv(1, vslot, j == 0, q);
+          }
+          commit(&p_free[1]);
+          release_slot(vslot);
+          if (!more) commit(&s_full[1]);
+          pph ^= 1;
+          ATT_TR(0, 4);
+        }
+      } else {
       const bool split = k2Cta && p.split_s;
       if (split) {
         if constexpr (k2Cta) {
@@ -484,13 +554,29 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         pph ^= 1;
         ATT_TR(0, 4);
       }
+      }  // !kSharedS
     }
   } else {
     // ===== softmax warpgroups (warps 0-3: tile A, warps 4-7: tile B) =====
     const int t = warp >> 2;
     const uint32_t lane_base = ((warp & 3u) * 32u) << 16;
-    const uint32_t tS = tmem_base + lane_base + t * 128;
+    const uint32_t tSr = tmem_base + lane_base + (kSharedS ? 0 : t * 128);             // S is read from here
+    const uint32_t tS = tmem_base + lane_base + (kSharedS ? 128 + t * 64 : t * 128);   // P is stored here
     const uint32_t tO = tmem_base + lane_base + 256 + t * 128;
+    bool pf_waited = true;  // kSharedS: P.V_t(j-1) known complete (P_t reusable, O_t up to date)
+    int cur_j = 0;
+    // kSharedS: before P_t is overwritten or O_t touched in step j >= 1, P.V_t(j-1) must have completed (p_free is
+    // committed behind it; completion number pass * n_kv + j - 1 -> its parity).  Taken as late as possible: the last
+    // P.V quarter of step j-1 is only issued when this warp has finished step j-1.
+    auto ensure_pfree = [&]() {
+      if constexpr (kSharedS) {
+        if (!pf_waited) {
+          mbar_wait_ns(&p_free[t], (uint32_t)((pass * n_kv + cur_j - 1) & 1), p.peer_timeout_ns);
+          tc_fence_after();
+          pf_waited = true;
+        }
+      }
+    };
     const float c = p.scale_log2;
     float ref = 0.0f;   // reference exponent (log2 units): the stored exponentials are 2^(s*c - ref)
     float l = 0.0f;     // running row sum (relative to ref)
@@ -499,7 +585,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     float pend = 0.0f;  // kMode 2: exponent shift to apply to ref / O / l before the next tile (0 = none)
     const bool tr = kTrace == 1 && (warp & 3) == 0 && lane == 0;
     auto rescale = [&](float alpha) {
-      // s_full(j) was committed after PV(j-1): O already holds every earlier contribution.
+      // s_full(j) was committed after PV(j-1): O already holds every earlier contribution (kSharedS: wait for it).
+      ensure_pfree();
       l *= alpha;
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
@@ -554,7 +641,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
     // split_s: columns 64..127 of this tile's S are in registers -> the MMA warp may compute S(j+1) of the upper 64 keys
     // into them (call once per tile, after the tcgen05.wait::ld that covered those columns)
     auto hi_read = [&]() {
-      if constexpr (k2Cta) {
+      if constexpr (kSharedS) {   // the whole S row is in registers: the MMA warp may overwrite the shared S buffer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(s_free);
+      } else if constexpr (k2Cta) {
         if (p.split_s) {
           tc_fence_before();
           __syncwarp();
@@ -563,6 +654,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       }
     };
     auto wait_s = [&](int j) {
+      cur_j = j;
+      pf_waited = (j == 0);
       if (tr) ATT_TR(1 + t, 0);
       mbar_wait_ns(&s_full[t], sphase, p.peer_timeout_ns);
       if (tr) ATT_TR(1 + t, 1);
@@ -575,7 +668,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       float ls[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t s[128];
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) tmem_ld32(tS + cc * 32, s + cc * 32);
+      for (int cc = 0; cc < 4; ++cc) tmem_ld32(tSr + cc * 32, s + cc * 32);
       tc_wait_ld();
       hi_read();
       if (tr) ATT_TR(1 + t, 2);
@@ -598,6 +691,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         ref = nref;
       }
       if (tr) ATT_TR(1 + t, 3);
+      ensure_pfree();
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t pk[32];
@@ -632,8 +726,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         plain = false;
       }
       uint32_t s[64], pk[32];
-      tmem_ld32(tS, s);
-      tmem_ld32(tS + 32, s + 32);
+      tmem_ld32(tSr, s);
+      tmem_ld32(tSr + 32, s + 32);
       tc_wait_ld();
       if (tr) ATT_TR(1 + t, 2);
       if (tr) ATT_TR(1 + t, 3);
@@ -665,14 +759,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           // second half of S is loaded into the registers the first half has already vacated, and the last release
           // leaves only two P.V k-steps (instead of four) between the end of the softmax and the next S MMA
           exp_pairs(I0{}, I16{});
+          ensure_pfree();
           tmem_st16(tS, pk);
-          tmem_ld32(tS + 64, s);            // s[0..31] are dead: S columns 64..95
+          tmem_ld32(tSr + 64, s);            // s[0..31] are dead: S columns 64..95
           exp_pairs(I16{}, I24{});
           release_part(0);
           if (tr) ATT_TR(1 + t, 4);
           exp_pairs(I24{}, I32{});
           tmem_st16(tS + 16, pk + 16);
-          tmem_ld32(tS + 96, s + 32);       // S columns 96..127
+          tmem_ld32(tSr + 96, s + 32);       // S columns 96..127
           tc_wait_ld();
           hi_read();
           exp_pairs(I0{}, I8{});
@@ -691,9 +786,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
           return;
         }
         exp_pairs(I0{}, I32{});
+        ensure_pfree();
         tmem_st32(tS, pk);
-        tmem_ld32(tS + 64, s);  // second half of the row
-        tmem_ld32(tS + 96, s + 32);
+        tmem_ld32(tSr + 64, s);  // second half of the row
+        tmem_ld32(tSr + 96, s + 32);
         if (p.st_overlap) {
           // the store of the first P half completes under the first 16 exponentials of the second half: its
           // tcgen05.wait::st (~150 clk when taken right after the store) no longer sits in this warp's critical path
@@ -720,9 +816,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
         const float neg = -ref;
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
         exp64(s, neg, pk, ls);
+        ensure_pfree();
         tmem_st32(tS, pk);
-        tmem_ld32(tS + 64, s);
-        tmem_ld32(tS + 96, s + 32);
+        tmem_ld32(tSr + 64, s);
+        tmem_ld32(tSr + 96, s + 32);
         release_half(0);
         if (tr) ATT_TR(1 + t, 4);
         tc_wait_ld();
@@ -834,7 +931,7 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
   }
   // G3C_ATTN_MODE: softmax variant (see k_attn_fwd), 2 = sum-guarded reference (default), 0 = exact max per tile;
   // G3C_ATTN_POLY=4: every 4th exponential on the FMA pipe (measured slower, kept for A/B runs)
-  static int poly = -1, mode = 2, cluster = 1, two_cta = 1;
+  static int poly = -1, mode = 2, cluster = 1, two_cta = 1, shared_s = 1;
   if (poly < 0) {
     const char* e = getenv("G3C_ATTN_POLY");
     poly = e ? atoi(e) : G3C_ATTN_POLY_DEFAULT;
@@ -842,6 +939,11 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<4, 0, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 0, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 1, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 0, 2, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 1, 2, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 2, 2, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    e = getenv("G3C_ATTN_SHAREDS");
+    shared_s = e ? atoi(e) != 0 : 1;
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 2, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     e = getenv("G3C_ATTN_2CTA");
     two_cta = e ? atoi(e) != 0 : 1;
@@ -947,7 +1049,11 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
         int rc = make_tmap_bf16_sw128(&tmV2, vt, 3, dims, str, box);
         if (rc) return rc;
       }
-      if (trace_level == 1) G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 1, 2, true, true>, tmQ, tmK2, tmV2, p));
+      if (shared_s && !p.split_s) {
+        if (trace_level == 1) G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 1, 2, true, true, true>, tmQ, tmK2, tmV2, p));
+        else if (trace_level == 2) G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 2, 2, true, true, true>, tmQ, tmK2, tmV2, p));
+        else G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 0, 2, true, true, true>, tmQ, tmK2, tmV2, p));
+      } else if (trace_level == 1) G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 1, 2, true, true>, tmQ, tmK2, tmV2, p));
       else if (trace_level == 2) G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 2, 2, true, true>, tmQ, tmK2, tmV2, p));
       else G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 0, 2, true, true>, tmQ, tmK2, tmV2, p));
     } else {
