@@ -401,62 +401,74 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
       uint32_t kslot = slot;
       advance();
       if constexpr (kSharedS) {
-        // every S computation except the very first waits for the previous one (the other tile's) to have been read
-        auto wait_s_free = [&]() {
-          mbar_wait_ns(s_free, sfp, p.peer_timeout_ns);
-          sfp ^= 1;
-          tc_fence_after();
-        };
-        if (pass != 0) wait_s_free();
-        mma_s(0, kslot);
-        commit(&s_full[0]);
-        wait_s_free();
-        mma_s(1, kslot);
-        commit(&s_full[1]);
-        release_slot(kslot);
-        for (int j = 0; j < n_kv; ++j) {
-          const bool more = j + 1 < n_kv;
-          mbar_wait_ns(&kv_full[slot], phase, p.peer_timeout_ns);  // V_j
-          const uint32_t vslot = slot;
-          advance();
-          ATT_TR(0, 0);
-          if (more) {
-            mbar_wait_ns(&kv_full[slot], phase, p.peer_timeout_ns);  // K_{j+1}
-            kslot = slot;
-            advance();
-            wait_s_free();                 // tile B has S_B(j) in registers
-            mma_s(0, kslot);               // S_A(j+1): under the exponentials of softmax A(j)
-            commit(&s_full[0]);
+        // Dynamic issue order.  The tensor pipe executes in issue order, and what the softmax warps wait for is the next
+        // S; a static order (S_A, P.V_A quarters, S_B, P.V_B quarters) parks S behind P.V work and blocks the issuing
+        // thread on one tile's P while the other tile's work is ready (measured: period 4 095 clk, the two softmaxes
+        // strictly alternating).  Here the thread polls (mbarrier.test_wait) and issues whatever is ready, S first:
+        //   S #i (tile i & 1, step i >> 1): K of that step loaded, and S #(i-1) read by its softmax (s_free);
+        //   P.V quarter q of tile t, step j: V_j loaded and p_part[t][q] of that step arrived.
+        // K_j sits in ring entry 2g, V_j in 2g + 1 with g = pass * n_kv + j (the loader's order).
+        (void)kslot;
+        const int g0 = pass * n_kv;
+        // a phase only moves forward: if any lane saw it complete it is complete (and the vote keeps the flow uniform)
+        auto done = [&](uint64_t* bar, uint32_t parity) { return __any_sync(0xffffffffu, mbar_test(bar, parity)) != 0; };
+        auto ring_ready = [&](int r) { return done(&kv_full[r % kSlots], (uint32_t)((r / kSlots) & 1)); };
+        int s_idx = 0;                    // next S computation of this pass
+        int pv_j[2] = {0, 0}, pv_q[2] = {0, 0};
+        int v_done[2] = {0, 0};           // steps whose P.V is fully issued, per tile
+        const int n_s = 2 * n_kv;
+        uint32_t spins = 0;
+        uint64_t t_first = 0;
+        // consumed the prologue wait on K_0 above through `slot`/`phase`; the dynamic loop indexes the ring itself
+        while (s_idx < n_s || pv_j[0] < n_kv || pv_j[1] < n_kv) {
+          bool progressed = false;
+          if (s_idx < n_s) {
+            const int tile = s_idx & 1, step = s_idx >> 1;
+            const bool first_ever = (pass == 0 && s_idx == 0);
+            if (ring_ready(2 * (g0 + step)) && (first_ever || done(s_free, sfp))) {
+              if (!first_ever) sfp ^= 1;
+              tc_fence_after();
+              mma_s(tile, (uint32_t)((2 * (g0 + step)) % kSlots));
+              commit(&s_full[tile]);
+              if (tile == 1) release_slot((uint32_t)((2 * (g0 + step)) % kSlots));
+              ++s_idx;
+              progressed = true;
+            }
           }
+          if (!progressed) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            mbar_wait_ns(&p_part[q], pph, p.peer_timeout_ns);
-            if (q == 0) ATT_TR(0, 1);
-            tc_fence_after();
-            mma_pv(0, vslot, j == 0, q);
+            for (int t = 0; t < 2; ++t) {
+              if (pv_j[t] < n_kv) {
+                const int j = pv_j[t], q = pv_q[t];
+                const int rv = 2 * (g0 + j) + 1;
+                if (ring_ready(rv) && done(&p_part[4 * t + q], (uint32_t)((g0 + j) & 1))) {
+                  tc_fence_after();
+                  mma_pv(t, (uint32_t)(rv % kSlots), j == 0, q);
+                  if (q == 3) {
+                    commit(&p_free[t]);
+                    if (j + 1 == n_kv) commit(&s_full[t]);   // epilogue: O_t complete
+                    v_done[t] = j + 1;
+                    if (v_done[t ^ 1] > j) release_slot((uint32_t)(rv % kSlots));  // both tiles are through with V_j
+                    pv_q[t] = 0;
+                    pv_j[t] = j + 1;
+                  } else {
+                    pv_q[t] = q + 1;
+                  }
+                  progressed = true;
+                }
+              }
+            }
           }
-          commit(&p_free[0]);
-          if (!more) commit(&s_full[0]);   // epilogue: O_A complete
-          ATT_TR(0, 2);
-          if (more) {
-            wait_s_free();                 // tile A has S_A(j+1) in registers
-            mma_s(1, kslot);
-            commit(&s_full[1]);
-            release_slot(kslot);
+          if (!progressed && (++spins & 0x3FFFu) == 0) {
+            const uint64_t now = global_timer_ns();
+            if (t_first == 0) t_first = now;
+            else if (now - t_first > p.peer_timeout_ns) asm volatile("trap;\n");
           }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            mbar_wait_ns(&p_part[4 + q], pph, p.peer_timeout_ns);
-            if (q == 0) ATT_TR(0, 3);
-            tc_fence_after();
-            mma_pv(1, vslot, j == 0, q);
-          }
-          commit(&p_free[1]);
-          release_slot(vslot);
-          if (!more) commit(&s_full[1]);
-          pph ^= 1;
-          ATT_TR(0, 4);
+          if (progressed) t_first = 0;
         }
+        // keep the (unused) in-order ring cursor consistent for a possible second pass
+        for (int r = 0; r < 2 * n_kv - 1; ++r) advance();
+        pph = (uint32_t)((g0 + n_kv) & 1);
       } else {
       const bool split = k2Cta && p.split_s;
       if (split) {
@@ -943,7 +955,7 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 1, 2, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 2, 2, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     e = getenv("G3C_ATTN_SHAREDS");
-    shared_s = e ? atoi(e) != 0 : 1;
+    shared_s = e ? atoi(e) != 0 : 0;
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 2, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     e = getenv("G3C_ATTN_2CTA");
     two_cta = e ? atoi(e) != 0 : 1;

@@ -107,6 +107,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #endif
   return ok != 0;
 }
+// non-blocking phase test (no suspend): true once the phase with this parity has completed
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Spin with a generous bound so that a protocol bug traps instead of hanging the GPU box.
 #ifndef G3C_MBAR_TIMEOUT_NS
 #define G3C_MBAR_TIMEOUT_NS 4000000000ull
