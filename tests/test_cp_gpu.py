@@ -125,4 +125,4 @@ def test_sharded_denoise_step_matches_unsharded(layout):
         p.join(timeout=60)
         assert p.exitcode == 0
     print(layout, res)
-    assert res["net_output_rel_l2_max_over_ranks"] < res["tol"] and res["x_next_rel_l2_max_over_ranks"] < 1e-3
+    assert res["net_output_rel_l2_max_over_ranks"] < res["tol"] and res["x_next_rel_l2_max_over_ranks"] < res["tol_x"]
