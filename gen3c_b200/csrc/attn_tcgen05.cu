@@ -906,6 +906,862 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
   }
 }
 
+// =====================================================================================================================
+// k_attn_fwd16 — the 2-CTA kernel above with SIXTEEN softmax warps: every 128x128 S tile is exponentiated by two warps
+// per TMEM lane quadrant, each owning 64 of the 128 keys of its 32 rows.
+//
+// Why: the exponentials are MUFU-bound, and ONE warp per sub-partition cannot saturate that pipe — 10.8 clk per element for
+// the loop `2 MUFU.EX2, FADD2, F2FP` issued by a lone warp against 8.7 clk when two warps of the sub-partition interleave
+// (profiles/r01_issue_rates_microbench.txt).  In k_attn_fwd the two tiles alternate strictly (tile A exponentiates while
+// tile B's MMAs run), so at any time a sub-partition had exactly one exponentiating warp: softmax(tile) ~ 1 500 clk against
+// the 1 024 clk of MMA work it overlaps, tensor pipe 62 % busy.  Two warps per quadrant bring a tile's softmax to
+// ~64 x 8.7 + load/store latency, and each warp's registers hold half a row (no 64-column software pipelining needed).
+//
+// What it takes:
+//  * TMEM lane quadrant q is only accessible to warps with warp % 4 == q, so the split is by COLUMNS: warp (t, h, q) owns
+//    keys [64h, 64h + 64) of rows [32q, 32q + 32) of tile t.  Its partner (t, h ^ 1, q) holds the same rows.
+//  * P (bf16, 64 columns) sits at columns [32, 96) of its S tile: the lower-half warp overwrites S columns 32..63 (its
+//    own, already in registers), the upper-half warp S columns 64..95 (its own) — no cross-warp hazard, no barrier.
+//  * the reference-free fast tiles need nothing from the partner.  The sum guard (row sum of a tile > 2^40 -> shift the
+//    reference by its exponent before the next tile) must take the same decision in both warps of a row: the warp that
+//    sees its partial sum exceed the bound posts (tile << 8 | exponent) with atomicMax into a per-row slot (two slots by
+//    tile parity; posted BEFORE the warp's last P release, read after the next s_full wait, so the mbarrier chain
+//    P release -> MMA -> commit -> s_full orders it), and both warps read the slot at the start of every fast tile.
+//  * exact tiles (tile 0 of every CTA, the exact mode, the second pass) exchange their partial row maxima through
+//    shared memory with a 64-thread named barrier per (tile, quadrant) pair; the final row sums likewise.
+//  * O rescales (rare) and the epilogue are split by columns as well (64 of the 128 head dimensions per warp); after a
+//    rescale the pair synchronises before either warp releases P, because a P.V MMA updates all 128 columns of O.
+// The loader and the MMA issuer are those of k_attn_fwd<.., k2Cta = true> (P released in four 32-key quarters: quarters
+// 0, 1 come from the lower-half warps, 2, 3 from the upper-half warps, 8 arrivals per barrier as before).
+constexpr int ATT16_THREADS = 576;           // warps 0-15 softmax, 16 loader, 17 MMA issuer / TMEM allocator
+constexpr int ATT16_XCH = 8192;              // row-max / row-sum exchange + sum-guard slots
+constexpr int ATT16_SMEM = ATT_SMEM + ATT16_XCH;
+
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;\n" ::"r"(id) : "memory"); }
+
+template <int kTrace, int kMode>
+__global__ void __launch_bounds__(ATT16_THREADS, 1)
+    k_attn_fwd16(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  constexpr int kSlots = 2 * ATT_SLOTS;
+  constexpr int kSlotBytes = ATT_TILE_BYTES / 2;
+  constexpr int kKvHalf = kSlotBytes / 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_q = smem;
+  uint8_t* smem_kv = smem + 2 * ATT_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + kSlots * kSlotBytes);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = bars + 1 + kSlots;
+  uint64_t* s_full = bars + 1 + 2 * kSlots;
+  uint64_t* p_part = bars + 3 + 2 * kSlots;       // [tile][key quarter]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11 + 2 * kSlots);
+  uint32_t* redo_flag = tmem_ptr + 1;
+  float* xmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [step parity][tile][half][128]
+  float* xsum = xmax + 2 * 2 * 2 * 128;                                            // [tile][half][128]
+  int* guard = reinterpret_cast<int*>(xsum + 2 * 2 * 128);                         // [step parity][tile][128]
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * 2 * ATT_TILE;
+  const int n_kv = p.Lk / ATT_TILE;
+
+  if (warp == 16 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 2);
+    for (int i = 0; i < kSlots; ++i) {
+      mbar_init(&kv_full[i], 2);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      for (int q = 0; q < 4; ++q) mbar_init(&p_part[4 * i + q], 8);  // 4 warps of the owning half, in both CTAs
+    }
+    *redo_flag = 0u;
+    fence_barrier_init();
+  }
+  if (warp == 17) tmem_alloc_2sm(tmem_ptr, 512);
+  if (threadIdx.x < 2 * 2 * 128) guard[threadIdx.x] = 0;
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t crank = cluster_ctarank();
+
+  uint32_t slot = 0, phase = 0;
+  uint32_t pph = 0;
+  uint32_t sphase = 0;
+  int pass = 0;
+  for (;;) {
+  const bool exact = kMode != 2 || pass == 1;
+  if (warp == 16) {
+    if (lane == 0) {
+      // ===== TMA producer (as k_attn_fwd, 2-CTA) =====
+      if (pass == 0) {
+        if (crank == 0) mbar_expect_tx(q_full, 4 * ATT_TILE_BYTES);
+        else mbar_arrive_leader(q_full);
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d_2sm(smem_q + t * ATT_TILE_BYTES + h * ATT_HALF_BYTES, &tmQ, q_full, head * 128 + h * 64,
+                            q0 + t * ATT_TILE);
+      }
+      const int tiles_per_chunk = p.vt_chunk_len / ATT_TILE;
+      const int n_chunks = p.Lk / p.vt_chunk_len;
+      for (int j = 0; j < n_kv; ++j) {
+        int chunk = p.first_chunk + j / tiles_per_chunk;
+        if (chunk >= n_chunks) chunk -= n_chunks;
+        const int within = j % tiles_per_chunk;
+        if (p.chunk_flags && within == 0 && chunk != p.first_chunk) {
+          uint32_t v, spins = 0;
+          uint64_t t0 = 0;
+          for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p.chunk_flags + chunk) : "memory");
+            if ((int)(v - p.flag_seq) >= 0) break;
+            if (t0 == 0) t0 = global_timer_ns();
+            if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > p.peer_timeout_ns) asm volatile("trap;\n");
+          }
+          if (t0 != 0 && p.wait_ns) atomicAdd(p.wait_ns, (unsigned long long)(global_timer_ns() - t0));
+          asm volatile("fence.proxy.async.global;\n" ::: "memory");
+        }
+        const int kv0 = chunk * p.vt_chunk_len + within * ATT_TILE;
+        mbar_wait_ns(&kv_empty[slot], phase ^ 1, p.peer_timeout_ns);
+        if (crank == 0) mbar_expect_tx(&kv_full[slot], 2 * kSlotBytes);
+        else mbar_arrive_leader(&kv_full[slot]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          tma_load_2d_2sm(smem_kv + slot * kSlotBytes + h * kKvHalf, &tmK, &kv_full[slot], head * 128 + h * 64,
+                          kv0 + (int)crank * 64);
+        if (++slot == kSlots) { slot = 0; phase ^= 1; }
+        mbar_wait_ns(&kv_empty[slot], phase ^ 1, p.peer_timeout_ns);
+        const int koff = within * ATT_TILE;
+        if (crank == 0) mbar_expect_tx(&kv_full[slot], 2 * kSlotBytes);
+        else mbar_arrive_leader(&kv_full[slot]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          tma_load_3d_2sm(smem_kv + slot * kSlotBytes + h * kKvHalf, &tmV, &kv_full[slot], koff + h * 64,
+                          head * 128 + (int)crank * 64, chunk);
+        if (++slot == kSlots) { slot = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 17) {
+    if (crank == 0) {
+      // ===== MMA issuer (converged warp, elected lane; as k_attn_fwd 2-CTA with P at S + 32) =====
+      const bool issuer = elect_one();
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(256, 128);
+      const uint32_t tS[2] = {tbase, tbase + 128};
+      const uint32_t tPa[2] = {tbase + 32, tbase + 128 + 32};
+      const uint32_t tO[2] = {tbase + 256, tbase + 384};
+      auto advance = [&]() { if (++slot == kSlots) { slot = 0; phase ^= 1; } };
+      auto commit = [&](uint64_t* bar) { if (issuer) umma_commit_2sm(bar); };
+      auto mma_s = [&](int t, uint32_t kslot) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t half = k >> 2, off = (k & 3) * 32;
+          uint64_t da = make_sdesc_sw128(smem_u32(smem_q + t * ATT_TILE_BYTES + half * ATT_HALF_BYTES));
+          uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + kslot * kSlotBytes + half * kKvHalf));
+          if (issuer) umma_ss_2sm(tS[t], sdesc_advance(da, off), sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
+        }
+      };
+      auto mma_pv = [&](int t, uint32_t vslot, bool first, int qq) {
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const int k = qq * 2 + kk;
+          const uint32_t half = k >> 2, off = (k & 3) * 32;
+          uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + vslot * kSlotBytes + half * kKvHalf));
+          if (issuer) umma_ts_2sm(tO[t], tPa[t] + k * 8, sdesc_advance(db, off), idesc, (first && k == 0) ? 0u : 1u);
+        }
+      };
+      if (pass == 0) mbar_wait_ns(q_full, 0, p.peer_timeout_ns);
+      mbar_wait_ns(&kv_full[slot], phase, p.peer_timeout_ns);
+      tc_fence_after();
+      uint32_t kslot = slot;
+      advance();
+      mma_s(0, kslot);
+      commit(&s_full[0]);
+      mma_s(1, kslot);
+      commit(&s_full[1]);
+      commit(&kv_empty[kslot]);
+      for (int j = 0; j < n_kv; ++j) {
+        const bool more = j + 1 < n_kv;
+        mbar_wait_ns(&kv_full[slot], phase, p.peer_timeout_ns);  // V_j
+        const uint32_t vslot = slot;
+        advance();
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          if (t == 0) ATT_TR(0, 0);
+          // quarters 0/1 (lower-half warps) and 2/3 (upper-half warps) become ready pairwise at about the same time
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            mbar_wait_ns(&p_part[4 * t + q], pph, p.peer_timeout_ns);
+            if (t == 0 && q == 0) ATT_TR(0, 1);
+            if (t == 1 && q == 0) ATT_TR(0, 3);
+            tc_fence_after();
+            mma_pv(t, vslot, j == 0, q);
+          }
+          if (t == 1) commit(&kv_empty[vslot]);
+          if (more) {
+            if (t == 0) {
+              mbar_wait_ns(&kv_full[slot], phase, p.peer_timeout_ns);  // K_{j+1}
+              tc_fence_after();
+              kslot = slot;
+              advance();
+            }
+            mma_s(t, kslot);
+          }
+          commit(&s_full[t]);
+          if (t == 0) ATT_TR(0, 2);
+          if (t == 1 && more) commit(&kv_empty[kslot]);
+        }
+        pph ^= 1;
+        ATT_TR(0, 4);
+      }
+    }
+  } else {
+    // ===== softmax: warp = 8 t + 4 h + quadrant =====
+    const int t = warp >> 3, h = (warp >> 2) & 1, quad = warp & 3;
+    const uint32_t lane_base = ((uint32_t)quad * 32u) << 16;
+    const int rowl = quad * 32 + (int)lane;                                      // row inside the tile
+    const uint32_t tSr = tmem_base + lane_base + t * 128 + h * 64;              // this thread's 64 S columns
+    const uint32_t tP = tmem_base + lane_base + t * 128 + 32 + h * 32;          // its 32 P columns (keys 64h..64h+63)
+    const uint32_t tO = tmem_base + lane_base + 256 + t * 128 + h * 64;         // its 64 O columns
+    const int pair_id = 1 + t * 4 + quad;                                       // named barrier of the (lower, upper) pair
+    const float c = p.scale_log2;
+    float ref = 0.0f, l = 0.0f;
+    bool ovf = false, plain = false;
+    const bool tr = kTrace == 1 && quad == 0 && h == 0 && lane == 0;
+    auto rescale = [&](float alpha) {
+      // both warps of the pair take this path together (same per-row decision); a P.V MMA of this step updates all 128
+      // columns of O, so neither may release P before the other has finished its columns
+      l *= alpha;
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t o[32];
+        tmem_ld32(tO + cc * 32, o);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st32(tO + cc * 32, o);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      pair_barrier(pair_id);
+      tc_fence_after();
+    };
+    auto release_part = [&](int q) {
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&p_part[4 * t + q]);
+    };
+    auto wait_s = [&](int j) {
+      if (tr) ATT_TR(1 + t, 0);
+      mbar_wait_ns(&s_full[t], sphase, p.peer_timeout_ns);
+      if (tr) ATT_TR(1 + t, 1);
+      sphase ^= 1;
+      tc_fence_after();
+    };
+    // exponentials of this thread's 64 keys (s) -> P (two 32-key quarters) ; returns the partial row sum.  `before_last`
+    // runs between the last P store and its release (sum guard: must be ordered before the release).
+    auto tile_body = [&](auto plain_c, uint32_t* s, float neg, int j, auto&& before_last) {
+      constexpr bool kPlain = decltype(plain_c)::value;
+      uint64_t ls2[2] = {0ull, 0ull};
+      uint32_t pk[32];
+      auto exp_pairs = [&](auto lo, auto hi) {
+#pragma unroll
+        for (int i = decltype(lo)::value; i < decltype(hi)::value; ++i) {
+          float a, b;
+          if constexpr (kPlain) {
+            a = ex2_approx(__uint_as_float(s[2 * i]));
+            b = ex2_approx(__uint_as_float(s[2 * i + 1]));
+          } else {
+            a = ex2_approx(fmaf(__uint_as_float(s[2 * i]), c, neg));
+            b = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), c, neg));
+          }
+          ls2[i & 1] = fadd2(ls2[i & 1], pack2(a, b));
+          pk[i] = pack_bf16x2(a, b);
+        }
+      };
+      using I0 = std::integral_constant<int, 0>;
+      using I16 = std::integral_constant<int, 16>;
+      using I24 = std::integral_constant<int, 24>;
+      using I32 = std::integral_constant<int, 32>;
+      exp_pairs(I0{}, I16{});
+      tmem_st16(tP, pk);
+      exp_pairs(I16{}, I24{});          // the store completes under these
+      release_part(2 * h);
+      if (tr) ATT_TR(1 + t, 4);
+      exp_pairs(I24{}, I32{});
+      tmem_st16(tP + 16, pk + 16);
+      float s0, s1, s2, s3;
+      unpack2(ls2[0], s0, s1);
+      unpack2(ls2[1], s2, s3);
+      const float tsum = (s0 + s1) + (s2 + s3);
+      before_last(tsum);
+      if (tr) ATT_TR(1 + t, 5);
+      release_part(2 * h + 1);
+      if (tr) ATT_TR(1 + t, 6);
+      return tsum;
+    };
+    auto nothing = [](float) {};
+    // exact tile: partial row max of 64 keys, exchanged with the partner; lazy rescale; exponentials
+    auto tile_exact = [&](int j) {
+      wait_s(j);
+      uint32_t s[64];
+      tmem_ld32(tSr, s);
+      tmem_ld32(tSr + 32, s + 32);
+      tc_wait_ld();
+      if (tr) ATT_TR(1 + t, 2);
+      float mxs[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mxs[i] = __uint_as_float(s[i]);
+#pragma unroll
+      for (int i = 8; i < 64; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], __uint_as_float(s[i]));
+      const float part = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                               fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+      // buffers alternate with the step parity: the next write to this one (step j + 2) lies behind the pair barrier of
+      // step j + 1, which the partner only reaches after this step's read
+      float* xb = xmax + (((j & 1) * 2 + t) * 2) * 128;
+      xb[h * 128 + rowl] = part;
+      pair_barrier(pair_id);
+      const float mxl = c * fmaxf(part, xb[(h ^ 1) * 128 + rowl]);
+      if (j == 0) {
+        plain = !exact && p.unit_scale && __all_sync(0xffffffffu, fabsf(mxl) <= 40.0f);
+        ref = plain ? 0.0f : mxl;
+      } else if (__any_sync(0xffffffffu, mxl - ref > 8.0f)) {
+        const float nref = fmaxf(ref, mxl);
+        rescale(ex2_approx(ref - nref));
+        ref = nref;
+        tmem_ld32(tSr, s);            // S is reloaded instead of being kept live across the rescale (register budget)
+        tmem_ld32(tSr + 32, s + 32);
+        tc_wait_ld();
+      }
+      if (tr) ATT_TR(1 + t, 3);
+      l += tile_body(std::false_type{}, s, -ref, j, nothing);
+    };
+    // fast tile (kMode 2, j > 0): no row max
+    auto tile_fast = [&](int j) {
+      wait_s(j);
+      uint32_t s[64];
+      tmem_ld32(tSr, s);
+      tmem_ld32(tSr + 32, s + 32);
+      // sum guard of the previous tile (posted by either warp of this row)
+      const int gv = *reinterpret_cast<volatile int*>(&guard[(((j - 1) & 1) * 2 + t) * 128 + rowl]);
+      const float pend = (gv >> 8) == j - 1 ? (float)(gv & 0xff) : 0.0f;
+      tc_wait_ld();
+      if (tr) ATT_TR(1 + t, 2);
+      if (__any_sync(0xffffffffu, pend != 0.0f)) {
+        rescale(__int_as_float((127 - (int)pend) << 23));  // exact power of two
+        ref += pend;
+        plain = false;
+        tmem_ld32(tSr, s);            // reloaded: keeping 64 S registers live across the rescale spills in the hot path
+        tmem_ld32(tSr + 32, s + 32);
+        tc_wait_ld();
+      }
+      if (tr) ATT_TR(1 + t, 3);
+      auto post_guard = [&](float tsum) {
+        if (tsum > 1.0995116e12f /* 2^40 */) {
+          const int e = ((__float_as_int(tsum) >> 23) & 0xff) - 127;   // inf -> 128 -> clamp 100: l is non-finite, second pass
+          atomicMax(&guard[((j & 1) * 2 + t) * 128 + rowl], (j << 8) | (e < 100 ? e : 100));
+        }
+      };
+      const float tsum = plain ? tile_body(std::true_type{}, s, 0.0f, j, post_guard)
+                               : tile_body(std::false_type{}, s, -ref, j, post_guard);
+      l += tsum;
+      ovf |= !(l < 1e27f);
+    };
+    if (exact) {
+#pragma unroll 1
+      for (int j = 0; j < n_kv; ++j) tile_exact(j);
+    } else {
+      tile_exact(0);
+#pragma unroll 1
+      for (int j = 1; j < n_kv; ++j) tile_fast(j);
+    }
+    // final: PV(n_kv-1) complete; total row sum = both halves
+    mbar_wait_ns(&s_full[t], sphase, p.peer_timeout_ns);
+    sphase ^= 1;
+    tc_fence_after();
+    xsum[(t * 2 + h) * 128 + rowl] = l;
+    pair_barrier(pair_id);
+    const float lt = l + xsum[(t * 2 + (h ^ 1)) * 128 + rowl];
+    if constexpr (kMode == 2) {
+      if (pass == 0 && (ovf || !(lt < 1e27f))) *reinterpret_cast<volatile uint32_t*>(redo_flag) = 1u;
+    }
+    const int row = q0 + t * ATT_TILE + rowl;
+    const float inv = 1.0f / lt;
+    __nv_bfloat16* optr = p.O + (size_t)row * p.ldo + head * 128 + h * 64;
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      uint32_t o[32];
+      tmem_ld32(tO + cc * 32, o);
+      tc_wait_ld();
+      if (row < p.Lq) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 q;
+          q.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+          q.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+          q.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+          q.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+          reinterpret_cast<uint4*>(optr + cc * 32)[i] = q;
+        }
+      }
+    }
+  }
+    if constexpr (kMode != 2) {
+      break;
+    } else {
+      tc_fence_before();
+      __syncthreads();
+      if (threadIdx.x == 0 && pass == 0 && *reinterpret_cast<volatile uint32_t*>(redo_flag) != 0u)
+        st_shared_cluster_u32(redo_flag, crank ^ 1u, 1u);
+      cluster_sync_all();
+      tc_fence_after();
+      if (pass == 1 || *reinterpret_cast<volatile uint32_t*>(redo_flag) == 0u) break;
+      pass = 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 17) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+// =====================================================================================================================
+// k_attn_fwd1t — ONE 128-row query tile per CTA (256 rows per 2-CTA pair), THREE S buffers in TMEM, software-pipelined:
+// the S MMA of KV step j + 3 is issued right behind the P.V MMA of step j, so the scores of the next steps are already
+// in TMEM when the softmax warps finish a step.
+//
+// Why: in the two-tile kernels above, P aliases its S tile and TMEM is full (2 S + 2 O), so per tile the chain
+// softmax(j) -> P.V(j) -> S(j+1) -> softmax(j+1) is strictly serial and the two tiles alternate: the tensor pipe idles
+// while a softmax runs longer than the other tile's MMAs (clock64 timelines in profiles/: period ~3 150 clk for
+// 2 x 1 024 clk of MMA work and 2 x 1 090 clk of MUFU work), and at any time only one tile's warps feed the MUFU pipe.
+// With one O accumulator (128 columns) three S buffers fit (384 columns): the softmax warps go from step to step
+// without waiting for any MMA in the steady state, the tensor pipe always has P.V(j-1) and S(j+2) queued, and the
+// step period tends to max(MUFU time, MMA time) of ONE tile.  The price is K / V traffic per query row (each CTA pair
+// now covers 256 rows instead of 512): 32 KB per CTA and step from L2, which ran at 12 % of its throughput before.
+//
+// Softmax: kSplit warps per TMEM lane quadrant, each owning 128 / kSplit keys of its 32 rows (two warps per
+// sub-partition saturate the MUFU pipe, one does not: profiles/r01_issue_rates_microbench.txt).  P (bf16) of key quarter
+// q lives in columns [32 q, 32 q + 16) of its S buffer — inside the S columns of the warp that produces it, so no
+// warp overwrites scores another warp still has to read; the P.V MMA takes one A address per 16-key k-step anyway.
+// Reference handling (kMode 2): tile 0 fixes the reference exponent (0 if all its row maxima are within 2^+-40 and S is
+// in log2 units); afterwards p = 2^(s - ref) with no row max.  A tile whose partial row sum exceeds 2^40 (or a running
+// sum beyond 1e27) makes the CTA pair repeat its sweep in the exact mode (row max per tile, lazy rescale) — the
+// two-tile kernels shift the reference instead, which needs a per-step rendezvous between the warps of a row that this
+// pipeline does not have.  Exact tiles exchange partial row maxima through shared memory (named barrier per quadrant).
+// A rescale of O waits for P.V(j-1) through the NEXT completion of s_full[(j-1) % 3]: the issuer commits that barrier
+// behind every P.V (with or without a new S MMA in front of it).
+template <int kSplit> struct Att1 {
+  static constexpr int kSoftmaxWarps = 4 * kSplit;
+  static constexpr int kThreads = 32 * (kSoftmaxWarps + 2);
+  static constexpr int kStages = 5;                              // ring of {K_{j+3} half, V_j half} pairs, 16 + 16 KB
+  static constexpr int kPartBytes = ATT_TILE_BYTES / 2;          // this CTA's half of a K / V^T tile
+  static constexpr int kStageBytes = 2 * kPartBytes;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kXchBytes = (2 * kSplit + kSplit) * 128 * 4;  // row-max exchange (two step parities) + row sums
+  static constexpr int kSmem = ATT_TILE_BYTES + kStages * kStageBytes + kBarBytes + kXchBytes + 1024;
+};
+
+__device__ __forceinline__ void group_barrier(int id, int threads) {
+  asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int kSplit, int kMode, int kTrace = 0, int kPoly = 0>   // kPoly = n > 0: every n-th pair of exponentials of the plain tiles on the FMA pipe
+__global__ void __launch_bounds__(Att1<kSplit>::kThreads, 1)
+    k_attn_fwd1t(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using C = Att1<kSplit>;
+  constexpr int kStages = C::kStages;
+  constexpr int kStageBytes = C::kStageBytes;
+  constexpr int kPartBytes = C::kPartBytes;
+  constexpr int kKvHalf = kPartBytes / 2;
+  constexpr int kLoader = C::kSoftmaxWarps, kIssuer = C::kSoftmaxWarps + 1;
+  constexpr int kKeys = ATT_TILE / kSplit;      // keys per softmax warp and step
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_q = smem;                        // [2 halves][128 x 128 B]
+  uint8_t* smem_kv = smem + ATT_TILE_BYTES;      // [stages]{K part [2 halves][64 x 128 B], V^T part [2 halves][64 x 128 B]}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + kStages * kStageBytes);
+  uint64_t* q_full = bars;                        // [1]
+  uint64_t* st_full = bars + 1;                   // [stages]
+  uint64_t* st_empty = bars + 1 + kStages;        // [stages]
+  uint64_t* s_full = bars + 1 + 2 * kStages;      // [3 buffers]: S ready, and every earlier MMA (P.V) complete
+  uint64_t* p_full = bars + 4 + 2 * kStages;      // [3 buffers]: P of the step stored by every softmax warp of the pair
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7 + 2 * kStages);
+  uint32_t* redo_flag = tmem_ptr + 1;
+  static_assert((7 + 2 * kStages + 1) * 8 <= C::kBarBytes, "barrier area");
+  float* xmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + C::kBarBytes);  // [step parity][kSplit][128]
+  float* xsum = xmax + 2 * kSplit * 128;                                                     // [kSplit][128]
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * ATT_TILE;
+  const int n_kv = p.Lk / ATT_TILE;
+
+  if (warp == kLoader && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 2);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&st_full[i], 2);
+      mbar_init(&st_empty[i], 1);
+    }
+    for (int b = 0; b < 3; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&p_full[b], 2 * C::kSoftmaxWarps);   // one elected arrive per softmax warp, of both CTAs
+    }
+    *redo_flag = 0u;
+    fence_barrier_init();
+  }
+  if (warp == kIssuer) tmem_alloc_2sm(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t crank = cluster_ctarank();
+
+  uint32_t slot = 0, phase = 0;  // KV ring position (loader: producer side, issuer: consumer side)
+  uint32_t pph = 0;              // issuer: bit b = parity of the next p_full[b] phase
+  uint32_t sph = 0;              // softmax warps: bit b = parity of the next s_full[b] phase
+  int pass = 0;
+  for (;;) {
+  const bool exact = kMode != 2 || pass == 1;
+  if (warp == kLoader) {
+    if (lane == 0) {
+      // ===== TMA producer: Q once, then K_0 K_1 K_2, V_0 K_3, V_1 K_4, ... (the issuer's consumption order) =====
+      if (pass == 0) {
+        if (crank == 0) mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);  // both CTAs' Q tiles
+        else mbar_arrive_leader(q_full);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          tma_load_2d_2sm(smem_q + h * ATT_HALF_BYTES, &tmQ, q_full, head * 128 + h * 64, q0);
+      }
+      const int tiles_per_chunk = p.vt_chunk_len / ATT_TILE;
+      const int n_chunks = p.Lk / p.vt_chunk_len;
+      auto locate = [&](int j, int& chunk, int& within) {
+        chunk = p.first_chunk + j / tiles_per_chunk;
+        if (chunk >= n_chunks) chunk -= n_chunks;
+        within = j % tiles_per_chunk;
+      };
+      // one ring stage = {K_jk, V_jv} (either may be absent: -1); ONE full / empty barrier pair per stage, so that the
+      // issuer spends one wait and one commit per KV step on the ring
+      auto fill = [&](int jk, int jv) {
+        mbar_wait_ns(&st_empty[slot], phase ^ 1, p.peer_timeout_ns);
+        const uint32_t parts = (jk >= 0 ? 1u : 0u) + (jv >= 0 ? 1u : 0u);
+        if (crank == 0) mbar_expect_tx(&st_full[slot], parts * 2 * kPartBytes);   // both CTAs' halves
+        else mbar_arrive_leader(&st_full[slot]);
+        uint8_t* st = smem_kv + slot * kStageBytes;
+        if (jk >= 0) {
+          int chunk, within;
+          locate(jk, chunk, within);
+          if (p.chunk_flags && within == 0 && chunk != p.first_chunk) {  // a remote chunk: wait for its producer rank
+            uint32_t v, spins = 0;
+            uint64_t t0 = 0;
+            for (;;) {
+              asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p.chunk_flags + chunk) : "memory");
+              if ((int)(v - p.flag_seq) >= 0) break;
+              if (t0 == 0) t0 = global_timer_ns();
+              if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > p.peer_timeout_ns) asm volatile("trap;\n");
+            }
+            if (t0 != 0 && p.wait_ns) atomicAdd(p.wait_ns, (unsigned long long)(global_timer_ns() - t0));
+            asm volatile("fence.proxy.async.global;\n" ::: "memory");
+          }
+          const int kv0 = chunk * p.vt_chunk_len + within * ATT_TILE;
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d_2sm(st + h * kKvHalf, &tmK, &st_full[slot], head * 128 + h * 64, kv0 + (int)crank * 64);
+        }
+        if (jv >= 0) {   // V_jv's chunk flag was checked when K_jv was loaded (three stages earlier)
+          int chunk, within;
+          locate(jv, chunk, within);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            tma_load_3d_2sm(st + kPartBytes + h * kKvHalf, &tmV, &st_full[slot], within * ATT_TILE + h * 64,
+                            head * 128 + (int)crank * 64, chunk);
+        }
+        if (++slot == kStages) { slot = 0; phase ^= 1; }
+      };
+      for (int j = 0; j < 3 && j < n_kv; ++j) fill(j, -1);
+      for (int j = 0; j < n_kv; ++j) fill(j + 3 < n_kv ? j + 3 : -1, j);
+    }
+  } else if (warp == kIssuer) {
+    if (crank == 0) {
+      // ===== MMA issuer: converged warp, one elected lane issues for both SMs =====
+      const bool issuer = elect_one();
+      const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+      constexpr uint32_t idesc = make_idesc_bf16(256, 128);
+      const uint32_t tO = tbase;
+      auto advance = [&]() { if (++slot == kStages) { slot = 0; phase ^= 1; } };
+      auto commit = [&](uint64_t* bar) { if (issuer) umma_commit_2sm(bar); };
+      auto mma_s = [&](uint32_t b, uint32_t st) {   // S buffer b = Q K^T : 8 k-steps over the head dimension
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t half = k >> 2, off = (k & 3) * 32;
+          uint64_t da = make_sdesc_sw128(smem_u32(smem_q + half * ATT_HALF_BYTES));
+          uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + st * kStageBytes + half * kKvHalf));
+          if (issuer) umma_ss_2sm(tbase + 128 + b * 128, sdesc_advance(da, off), sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
+        }
+      };
+      auto mma_pv = [&](uint32_t b, uint32_t st, bool first) {   // O += P V : 8 k-steps of 16 keys; P quarter q at column 32 q
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t half = k >> 2, off = (k & 3) * 32;
+          uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + st * kStageBytes + kPartBytes + half * kKvHalf));
+          if (issuer)
+            umma_ts_2sm(tO, tbase + 128 + b * 128 + (k >> 1) * 32 + (k & 1) * 8, sdesc_advance(db, off), idesc,
+                        (first && k == 0) ? 0u : 1u);
+        }
+      };
+      if (pass == 0) mbar_wait_ns(q_full, 0, p.peer_timeout_ns);
+      for (int j = 0; j < 3 && j < n_kv; ++j) {
+        mbar_wait_ns(&st_full[slot], phase, p.peer_timeout_ns);  // K_j
+        tc_fence_after();
+        mma_s((uint32_t)j, slot);
+        commit(&s_full[j]);
+        commit(&st_empty[slot]);
+        advance();
+      }
+      // steady state, per KV step: two waits, 8 P.V + 8 S MMAs back to back, two commits back to back (a tcgen05.commit
+      // costs the issuing thread ~80 clk: with five per step — per-tile ring entries, per-quarter P barriers — this loop
+      // took 1 395 clk per step against 1 024 clk of MMA work, clock64 timeline in profiles/r02_attn_trace_1t.txt)
+      uint32_t b = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        ATT_TR(0, 0);
+        mbar_wait_ns(&st_full[slot], phase, p.peer_timeout_ns);  // V_j (and K_{j+3})
+        ATT_TR(0, 1);
+        mbar_wait_ns(&p_full[b], (pph >> b) & 1u, p.peer_timeout_ns);
+        pph ^= 1u << b;
+        ATT_TR(0, 2);
+        tc_fence_after();
+        mma_pv(b, slot, j == 0);
+        ATT_TR(0, 3);
+        if (j + 3 < n_kv) mma_s(b, slot);
+        ATT_TR(0, 4);
+        commit(&s_full[b]);     // S(j+3) ready / P.V(j) complete (consumed by a rescale of step j+1 and by the epilogue)
+        commit(&st_empty[slot]);
+        ATT_TR(0, 5);
+        advance();
+        b = b == 2 ? 0 : b + 1;
+      }
+    }
+  } else {
+    // ===== softmax: warp = 4 h + quadrant, keys [kKeys h, kKeys h + kKeys) of rows [32 quadrant, +32) =====
+    const int h = warp >> 2, quad = warp & 3;
+    const uint32_t lane_base = ((uint32_t)quad * 32u) << 16;
+    const int rowl = quad * 32 + (int)lane;
+    const uint32_t tSw = tmem_base + lane_base + 128 + h * kKeys;     // + 128 b: this thread's S columns (P: same base)
+    const uint32_t tO = tmem_base + lane_base + h * kKeys;            // its O columns
+    const int group_id = 1 + quad;
+    const float c = p.scale_log2;
+    float ref = 0.0f, l = 0.0f;
+    bool bad = false, plain = false;
+    auto wait_s = [&](uint32_t b) {
+      mbar_wait_ns(&s_full[b], (sph >> b) & 1u, p.peer_timeout_ns);
+      sph ^= 1u << b;
+      tc_fence_after();
+    };
+    auto release = [&](uint32_t b) {   // this warp's P columns of the step are in TMEM
+      tc_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&p_full[b]);
+    };
+    auto load_s = [&](uint32_t b, uint32_t* s) {
+#pragma unroll
+      for (int cc = 0; cc < kKeys / 32; ++cc) tmem_ld32(tSw + b * 128 + cc * 32, s + cc * 32);
+      tc_wait_ld();
+    };
+    // O *= alpha (this warp's columns) at step j >= 1: P.V(j-1) must be complete — the next completion of
+    // s_full[(j-1) % 3], waited for without consuming it.  The warps of the quadrant then synchronise: P.V(j) updates
+    // all 128 columns of O, so none may release P before all have rescaled.
+    auto rescale = [&](float alpha, uint32_t b) {
+      const uint32_t bp = b == 0 ? 2u : b - 1u;
+      mbar_wait_ns(&s_full[bp], (sph >> bp) & 1u, p.peer_timeout_ns);
+      tc_fence_after();
+      l *= alpha;
+#pragma unroll 1
+      for (int cc = 0; cc < kKeys / 32; ++cc) {
+        uint32_t o[32];
+        tmem_ld32(tO + cc * 32, o);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st32(tO + cc * 32, o);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      group_barrier(group_id, 32 * kSplit);
+      tc_fence_after();
+    };
+    // exponentials of this thread's keys -> P (key quarter q at column 32 q of the S buffer); returns the partial row sum
+    auto tile_body = [&](auto plain_c, uint32_t* s, float neg, uint32_t b) {
+      constexpr bool kPlain = decltype(plain_c)::value;
+      uint64_t ls2[2] = {0ull, 0ull};
+      uint32_t pk[kKeys / 2];
+      auto exp_pairs = [&](auto lo, auto hi) {
+#pragma unroll
+        for (int i = decltype(lo)::value; i < decltype(hi)::value; ++i) {
+          float a, b2;
+          if constexpr (kPlain) {
+            if (kPoly > 0 && (i % (kPoly > 0 ? kPoly : 1)) == (kPoly > 0 ? kPoly - 1 : 0)) {
+              ex2_poly2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]), a, b2);
+            } else {
+              a = ex2_approx(__uint_as_float(s[2 * i]));
+              b2 = ex2_approx(__uint_as_float(s[2 * i + 1]));
+            }
+          } else {
+            a = ex2_approx(fmaf(__uint_as_float(s[2 * i]), c, neg));
+            b2 = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), c, neg));
+          }
+          ls2[i & 1] = fadd2(ls2[i & 1], pack2(a, b2));
+          pk[i] = pack_bf16x2(a, b2);
+        }
+      };
+      using I0 = std::integral_constant<int, 0>;
+      using I16 = std::integral_constant<int, 16>;
+      const uint32_t tPw = tSw + b * 128;
+      exp_pairs(I0{}, I16{});
+      tmem_st16(tPw, pk);
+      if constexpr (kSplit == 2) {
+        using I32 = std::integral_constant<int, 32>;
+        exp_pairs(I16{}, I32{});          // the first store completes under these
+        tmem_st16(tPw + 32, pk + 16);
+      }
+      release(b);
+      float s0, s1, s2, s3;
+      unpack2(ls2[0], s0, s1);
+      unpack2(ls2[1], s2, s3);
+      return (s0 + s1) + (s2 + s3);
+    };
+    auto tile_exact = [&](int j, uint32_t b) {
+      wait_s(b);
+      uint32_t s[kKeys];
+      load_s(b, s);
+      float mxs[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mxs[i] = __uint_as_float(s[i]);
+#pragma unroll
+      for (int i = 8; i < kKeys; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], __uint_as_float(s[i]));
+      float part = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                         fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+      // exchange buffers alternate with the step parity: the next write to this one (step j + 2) lies behind the group
+      // barrier of step j + 1, which every warp of the quadrant reaches only after this step's reads
+      float* xb = xmax + (j & 1) * kSplit * 128;
+      xb[h * 128 + rowl] = part;
+      group_barrier(group_id, 32 * kSplit);
+#pragma unroll
+      for (int o = 1; o < kSplit; ++o) part = fmaxf(part, xb[((h + o) % kSplit) * 128 + rowl]);
+      const float mxl = c * part;
+      if (j == 0) {
+        plain = !exact && p.unit_scale && __all_sync(0xffffffffu, fabsf(mxl) <= 40.0f);
+        ref = plain ? 0.0f : mxl;
+      } else if (__any_sync(0xffffffffu, mxl - ref > 8.0f)) {   // same row values in every warp of the quadrant
+        const float nref = fmaxf(ref, mxl);
+        rescale(ex2_approx(ref - nref), b);
+        ref = nref;
+        load_s(b, s);   // reloaded rather than kept live across the rescale
+      }
+      l += tile_body(std::false_type{}, s, -ref, b);
+    };
+    const bool tr = kTrace && quad == 0 && lane == 0 && (h == 0 || h == kSplit - 1);
+    const int trole = h == 0 ? 1 : 2;
+    auto tile_fast = [&](uint32_t b, int j) {
+      if (tr) ATT_TR(trole, 0);
+      wait_s(b);
+      if (tr) ATT_TR(trole, 1);
+      uint32_t s[kKeys];
+      load_s(b, s);
+      if (tr) ATT_TR(trole, 2);
+      const float tsum = plain ? tile_body(std::true_type{}, s, 0.0f, b) : tile_body(std::false_type{}, s, -ref, b);
+      if (tr) ATT_TR(trole, 3);
+      l += tsum;
+      bad |= !(tsum < 1.0995116e12f /* 2^40 */);
+    };
+    {
+      uint32_t b = 0;
+      if (exact) {
+#pragma unroll 1
+        for (int j = 0; j < n_kv; ++j) { tile_exact(j, b); b = b == 2 ? 0 : b + 1; }
+      } else {
+        tile_exact(0, 0);
+        b = 1;
+#pragma unroll 1
+        for (int j = 1; j < n_kv; ++j) { tile_fast(b, j); b = b == 2 ? 0 : b + 1; }
+      }
+    }
+    // the issuer commits s_full behind every P.V: consume the completions of the last (up to three) steps; the last one
+    // says that O is final
+    for (int j = n_kv > 3 ? n_kv - 3 : 0; j < n_kv; ++j) wait_s((uint32_t)(j % 3));
+    xsum[h * 128 + rowl] = l;
+    group_barrier(group_id, 32 * kSplit);
+    float lt = l;
+#pragma unroll
+    for (int o = 1; o < kSplit; ++o) lt += xsum[((h + o) % kSplit) * 128 + rowl];
+    if constexpr (kMode == 2) {
+      if (pass == 0 && (bad || !(lt < 1e27f))) *reinterpret_cast<volatile uint32_t*>(redo_flag) = 1u;
+    }
+    const int row = q0 + rowl;
+    const float inv = 1.0f / lt;
+    __nv_bfloat16* optr = p.O + (size_t)row * p.ldo + head * 128 + h * kKeys;
+#pragma unroll 1
+    for (int cc = 0; cc < kKeys / 32; ++cc) {
+      uint32_t o[32];
+      tmem_ld32(tO + cc * 32, o);
+      tc_wait_ld();
+      if (row < p.Lq) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 q;
+          q.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+          q.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+          q.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+          q.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+          reinterpret_cast<uint4*>(optr + cc * 32)[i] = q;
+        }
+      }
+    }
+  }
+    if constexpr (kMode != 2) {
+      break;
+    } else {
+      tc_fence_before();
+      __syncthreads();
+      if (threadIdx.x == 0 && pass == 0 && *reinterpret_cast<volatile uint32_t*>(redo_flag) != 0u)
+        st_shared_cluster_u32(redo_flag, crank ^ 1u, 1u);
+      cluster_sync_all();
+      tc_fence_after();
+      if (pass == 1 || *reinterpret_cast<volatile uint32_t*>(redo_flag) == 0u) break;
+      pass = 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == kIssuer) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
 unsigned long long* g_attn_trace = nullptr;  // set through g3c_attn_set_trace (profiling aid, not a product path)
 
 int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, int Lk, int heads,
@@ -943,7 +1799,7 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
   }
   // G3C_ATTN_MODE: softmax variant (see k_attn_fwd), 2 = sum-guarded reference (default), 0 = exact max per tile;
   // G3C_ATTN_POLY=4: every 4th exponential on the FMA pipe (measured slower, kept for A/B runs)
-  static int poly = -1, mode = 2, cluster = 1, two_cta = 1, shared_s = 1;
+  static int poly = -1, mode = 2, cluster = 1, two_cta = 1, shared_s = 1, w16 = 0, one_tile = 4, poly1t = 4;
   if (poly < 0) {
     const char* e = getenv("G3C_ATTN_POLY");
     poly = e ? atoi(e) : G3C_ATTN_POLY_DEFAULT;
@@ -956,6 +1812,23 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 2, 2, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     e = getenv("G3C_ATTN_SHAREDS");
     shared_s = e ? atoi(e) != 0 : 0;
+    e = getenv("G3C_ATTN_W16");
+    w16 = e ? atoi(e) != 0 : 0;
+    e = getenv("G3C_ATTN_1T");   // one query tile per CTA, three S buffers: softmax warps per lane quadrant (0 = off)
+    one_tile = e ? atoi(e) : 4;
+    if (one_tile != 0 && one_tile != 2 && one_tile != 4) one_tile = 4;
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd1t<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att1<2>::kSmem));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd1t<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att1<4>::kSmem));
+    e = getenv("G3C_ATTN_POLY1T");   // 2 | 3 | 4: every n-th pair of exponentials on the FMA pipe (k_attn_fwd1t<4>)
+    poly1t = e ? atoi(e) : 4;   // in-step A/B on one box: 1/4 -> 0.2900 steps/s, none 0.2871, 1/3 0.2867, 1/2 0.2685
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd1t<4, 2, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att1<4>::kSmem));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd1t<4, 2, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att1<4>::kSmem));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd1t<4, 2, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att1<4>::kSmem));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd1t<2, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att1<2>::kSmem));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd1t<4, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att1<4>::kSmem));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd16<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT16_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd16<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT16_SMEM));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd16<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT16_SMEM));
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd<0, 2, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     e = getenv("G3C_ATTN_2CTA");
     two_cta = e ? atoi(e) != 0 : 1;
@@ -1061,7 +1934,44 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
         int rc = make_tmap_bf16_sw128(&tmV2, vt, 3, dims, str, box);
         if (rc) return rc;
       }
-      if (shared_s && !p.split_s) {
+      if (one_tile && trace_level && !p.split_s && !shared_s) {
+        cfg.gridDim = dim3((((unsigned)(Lq + ATT_TILE - 1) / ATT_TILE) + 1) & ~1u, grid.y);
+        if (one_tile == 4) {
+          cfg.blockDim = dim3(Att1<4>::kThreads);
+          cfg.dynamicSmemBytes = Att1<4>::kSmem;
+          G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd1t<4, 2, 1>, tmQ, tmK2, tmV2, p));
+        } else {
+          cfg.blockDim = dim3(Att1<2>::kThreads);
+          cfg.dynamicSmemBytes = Att1<2>::kSmem;
+          G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd1t<2, 2, 1>, tmQ, tmK2, tmV2, p));
+        }
+      } else if (one_tile && poly1t && !p.split_s && !shared_s) {
+        cfg.gridDim = dim3((((unsigned)(Lq + ATT_TILE - 1) / ATT_TILE) + 1) & ~1u, grid.y);
+        cfg.blockDim = dim3(Att1<4>::kThreads);
+        cfg.dynamicSmemBytes = Att1<4>::kSmem;
+        if (poly1t == 3) G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd1t<4, 2, 0, 3>, tmQ, tmK2, tmV2, p));
+        else if (poly1t == 2) G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd1t<4, 2, 0, 2>, tmQ, tmK2, tmV2, p));
+        else G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd1t<4, 2, 0, 4>, tmQ, tmK2, tmV2, p));
+      } else if (one_tile && !p.split_s && !shared_s) {
+        // default: one 128-row tile per CTA, three S buffers, software-pipelined (k_attn_fwd1t)
+        cfg.gridDim = dim3((((unsigned)(Lq + ATT_TILE - 1) / ATT_TILE) + 1) & ~1u, grid.y);
+        if (one_tile == 4) {
+          cfg.blockDim = dim3(Att1<4>::kThreads);
+          cfg.dynamicSmemBytes = Att1<4>::kSmem;
+          G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd1t<4, 2>, tmQ, tmK2, tmV2, p));
+        } else {
+          cfg.blockDim = dim3(Att1<2>::kThreads);
+          cfg.dynamicSmemBytes = Att1<2>::kSmem;
+          G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd1t<2, 2>, tmQ, tmK2, tmV2, p));
+        }
+      } else if (w16 && !p.split_s && !shared_s) {
+        // default: sixteen softmax warps (two per TMEM lane quadrant and tile, 64 keys each)
+        cfg.blockDim = dim3(ATT16_THREADS);
+        cfg.dynamicSmemBytes = ATT16_SMEM;
+        if (trace_level == 1) G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd16<1, 2>, tmQ, tmK2, tmV2, p));
+        else if (trace_level == 2) G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd16<2, 2>, tmQ, tmK2, tmV2, p));
+        else G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd16<0, 2>, tmQ, tmK2, tmV2, p));
+      } else if (shared_s && !p.split_s) {
         if (trace_level == 1) G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 1, 2, true, true, true>, tmQ, tmK2, tmV2, p));
         else if (trace_level == 2) G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 2, 2, true, true, true>, tmQ, tmK2, tmV2, p));
         else G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd<0, 0, 2, true, true, true>, tmQ, tmK2, tmV2, p));

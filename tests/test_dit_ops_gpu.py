@@ -151,6 +151,24 @@ def test_attention_score_jump(jump):
     assert rel(o, ref) < 5e-3, rel(o, ref)
 
 
+@pytest.mark.parametrize("first_key", [260, 330])
+def test_attention_score_jump_in_one_key_half(first_key):
+    """The default kernel exponentiates every 128-key tile with two warps per row (64 keys each).  A jump confined to the
+    lower (keys 260..291 = columns 4..35 of tile 2) or the upper (330..361 = columns 74..105) half makes only ONE of them
+    see its partial row sum exceed the guard: it must post the shift so that both halves (and both halves of O) move to
+    the same reference before the next tile."""
+    from gen3c_b200 import ops
+
+    heads, Lq, Lk = 2, 384, 2048
+    q, k, v = bf(Lq, heads * 128, seed=23, s=0.5), bf(Lk, heads * 128, seed=24, s=0.5), bf(Lk, heads * 128, seed=25)
+    q[:, :128] = 1.0
+    k[first_key:first_key + 32, :128] = 4.0
+    ref = sdpa_ref(q, k, v, heads)
+    o = ops.attention(q, k, v.T.contiguous(), heads)
+    assert torch.isfinite(o.float()).all()
+    assert rel(o, ref) < 5e-3, rel(o, ref)
+
+
 @pytest.mark.parametrize("gain", [1.0, 6.0])
 def test_attention_log2_units(gain):
     """scale = ln 2: the caller folded softmax_scale * log2(e) into Q (what the DiT engine does through the query
