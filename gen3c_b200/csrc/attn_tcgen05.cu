@@ -1799,7 +1799,7 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
   }
   // G3C_ATTN_MODE: softmax variant (see k_attn_fwd), 2 = sum-guarded reference (default), 0 = exact max per tile;
   // G3C_ATTN_POLY=4: every 4th exponential on the FMA pipe (measured slower, kept for A/B runs)
-  static int poly = -1, mode = 2, cluster = 1, two_cta = 1, shared_s = 1, w16 = 0, one_tile = 4, poly1t = 4;
+  static int poly = -1, mode = 2, cluster = 1, two_cta = 1, shared_s = 1, w16 = 0, one_tile = 4, poly1t = 4, short_1t = 0;
   if (poly < 0) {
     const char* e = getenv("G3C_ATTN_POLY");
     poly = e ? atoi(e) : G3C_ATTN_POLY_DEFAULT;
@@ -1819,6 +1819,8 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     if (one_tile != 0 && one_tile != 2 && one_tile != 4) one_tile = 4;
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd1t<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att1<2>::kSmem));
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd1t<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att1<4>::kSmem));
+    e = getenv("G3C_ATTN_SHORT1T");  // 1: short key ranges (cross-attention) on the pipelined kernel too
+    short_1t = e ? atoi(e) != 0 : 0;
     e = getenv("G3C_ATTN_POLY1T");   // 2 | 3 | 4: every n-th pair of exponentials on the FMA pipe (k_attn_fwd1t<4>)
     poly1t = e ? atoi(e) : 4;   // in-step A/B on one box: 1/4 -> 0.2900 steps/s, none 0.2871, 1/3 0.2867, 1/2 0.2685
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd1t<4, 2, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att1<4>::kSmem));
@@ -1894,7 +1896,7 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     if (mode && mo && atoi(mo)) k_attn_fwd<0, 2, 2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
     else if (mode) k_attn_fwd<0, 1, 2, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
     else k_attn_fwd<0, 1, 0, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
-  } else if (mode == 0 || Lk <= 8 * ATT_TILE) {
+  } else if (mode == 0 || (Lk <= 8 * ATT_TILE && !short_1t)) {
     // also the choice for short key ranges (cross-attention: 4 KV tiles): the CTA is prologue-bound there and the
     // cluster launch / second-pass agreement of the default path only add latency (0.72 vs 0.83 ms at 56 320 x 512)
     k_attn_fwd<0, 0, 0, false><<<grid, ATT_THREADS, ATT_SMEM, st>>>(tmQ, tmK, tmV, p);
@@ -1945,7 +1947,7 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
           cfg.dynamicSmemBytes = Att1<2>::kSmem;
           G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd1t<2, 2, 1>, tmQ, tmK2, tmV2, p));
         }
-      } else if (one_tile && poly1t && !p.split_s && !shared_s) {
+      } else if (one_tile == 4 && poly1t && !p.split_s && !shared_s) {
         cfg.gridDim = dim3((((unsigned)(Lq + ATT_TILE - 1) / ATT_TILE) + 1) & ~1u, grid.y);
         cfg.blockDim = dim3(Att1<4>::kThreads);
         cfg.dynamicSmemBytes = Att1<4>::kSmem;
