@@ -65,6 +65,7 @@ struct AttnParams {
   int split_s;                // 2-CTA kernel: S = Q K^T as two 64-key UMMAs; the upper one is issued for step j+1 as soon as
                               // the softmax has read columns 64..127 of S(j) (they do not alias P), i.e. under the
                               // exponentials and before P.V(j), which shortens the per-tile dependent chain by half an S MMA
+  int dbg_dup_loads;          // experiment (G3C_ATTN_DUP_LOADS): k_attn_fwd1t fetches every K / V part this many extra times
   unsigned long long* trace;  // kTrace only: [3 roles][64 steps][8 slots] clock64 stamps of CTA (0,0)
 };
 
@@ -1466,7 +1467,8 @@ __global__ void __launch_bounds__(Att1<kSplit>::kThreads, 1)
       auto fill = [&](int jk, int jv) {
         mbar_wait_ns(&st_empty[slot], phase ^ 1, p.peer_timeout_ns);
         const uint32_t parts = (jk >= 0 ? 1u : 0u) + (jv >= 0 ? 1u : 0u);
-        if (crank == 0) mbar_expect_tx(&st_full[slot], parts * 2 * kPartBytes);   // both CTAs' halves
+        const int reps = 1 + p.dbg_dup_loads;
+        if (crank == 0) mbar_expect_tx(&st_full[slot], reps * parts * 2 * kPartBytes);   // both CTAs' halves
         else mbar_arrive_leader(&st_full[slot]);
         uint8_t* st = smem_kv + slot * kStageBytes;
         if (jk >= 0) {
@@ -1485,17 +1487,19 @@ __global__ void __launch_bounds__(Att1<kSplit>::kThreads, 1)
             asm volatile("fence.proxy.async.global;\n" ::: "memory");
           }
           const int kv0 = chunk * p.vt_chunk_len + within * ATT_TILE;
+          for (int r = 0; r < reps; ++r)
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-            tma_load_2d_2sm(st + h * kKvHalf, &tmK, &st_full[slot], head * 128 + h * 64, kv0 + (int)crank * 64);
+            for (int h = 0; h < 2; ++h)
+              tma_load_2d_2sm(st + h * kKvHalf, &tmK, &st_full[slot], head * 128 + h * 64, kv0 + (int)crank * 64);
         }
         if (jv >= 0) {   // V_jv's chunk flag was checked when K_jv was loaded (three stages earlier)
           int chunk, within;
           locate(jv, chunk, within);
+          for (int r = 0; r < reps; ++r)
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-            tma_load_3d_2sm(st + kPartBytes + h * kKvHalf, &tmV, &st_full[slot], within * ATT_TILE + h * 64,
-                            head * 128 + (int)crank * 64, chunk);
+            for (int h = 0; h < 2; ++h)
+              tma_load_3d_2sm(st + kPartBytes + h * kKvHalf, &tmV, &st_full[slot], within * ATT_TILE + h * 64,
+                              head * 128 + (int)crank * 64, chunk);
         }
         if (++slot == kStages) { slot = 0; phase ^= 1; }
       };
@@ -1887,6 +1891,12 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
   }
   p.p_quarters = quarters && halves;
   G3C_REQUIRE(p.first_chunk >= 0 && p.first_chunk < Lk / vt_chunk_len, "attn: first chunk %d out of range", p.first_chunk);
+  static int dup_loads = -1;
+  if (dup_loads < 0) {
+    const char* e = getenv("G3C_ATTN_DUP_LOADS");
+    dup_loads = e ? atoi(e) : 0;
+  }
+  p.dbg_dup_loads = dup_loads;
   p.trace = g_attn_trace;
   const char* tmo = getenv("G3C_ATTN_TRACE_MMA_ONLY");
   const int trace_level = g_attn_trace ? ((tmo && atoi(tmo)) ? 2 : 1) : 0;
