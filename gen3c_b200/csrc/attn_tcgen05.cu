@@ -65,6 +65,9 @@ struct AttnParams {
   int split_s;                // 2-CTA kernel: S = Q K^T as two 64-key UMMAs; the upper one is issued for step j+1 as soon as
                               // the softmax has read columns 64..127 of S(j) (they do not alias P), i.e. under the
                               // exponentials and before P.V(j), which shortens the per-tile dependent chain by half an S MMA
+  const __nv_bfloat16* Q;     // k_attn_fwd1t<kQT>: Q rows are read straight from global memory into TMEM
+  int ldq;
+  int kv_rotate;              // k_attn_fwd1t: every CTA pair visits the KV tiles of a chunk from its own start offset
   int dbg_dup_loads;          // experiment (G3C_ATTN_DUP_LOADS): k_attn_fwd1t fetches every K / V part this many extra times
   unsigned long long* trace;  // kTrace only: [3 roles][64 steps][8 slots] clock64 stamps of CTA (0,0)
 };
@@ -1366,27 +1369,36 @@ __global__ void __launch_bounds__(ATT16_THREADS, 1)
 // pipeline does not have.  Exact tiles exchange partial row maxima through shared memory (named barrier per quadrant).
 // A rescale of O waits for P.V(j-1) through the NEXT completion of s_full[(j-1) % 3]: the issuer commits that barrier
 // behind every P.V (with or without a new S MMA in front of it).
-template <int kSplit> struct Att1 {
+// kQT: Q lives in TMEM (the A operand of the S MMA comes from TMEM like P does for P.V) instead of shared memory: its
+// 32 KB buy a sixth ring stage, at the price of the third S buffer (TMEM: O [0,128) Q [128,192) S [256,512)).  On most
+// boxes the K / V delivery — not the MMAs or the exponentials — set the step period of the 5-stage variant (issuer
+// waiting ~850 of 1 560 clk per step for the stage, i.e. ~4 us from TMA issue to arrival with 4 stages in flight).
+template <int kSplit, bool kQT = false> struct Att1 {
   static constexpr int kSoftmaxWarps = 4 * kSplit;
   static constexpr int kThreads = 32 * (kSoftmaxWarps + 2);
-  static constexpr int kStages = 5;                              // ring of {K_{j+3} half, V_j half} pairs, 16 + 16 KB
+  static constexpr int kBufs = kQT ? 2 : 3;                      // S buffers = look-ahead of the S MMAs in KV steps
+  static constexpr int kStages = kQT ? 6 : 5;                    // ring of {K_{j+kBufs} half, V_j half} pairs, 16 + 16 KB
   static constexpr int kPartBytes = ATT_TILE_BYTES / 2;          // this CTA's half of a K / V^T tile
   static constexpr int kStageBytes = 2 * kPartBytes;
   static constexpr int kBarBytes = 256;
   static constexpr int kXchBytes = (2 * kSplit + kSplit) * 128 * 4;  // row-max exchange (two step parities) + row sums
-  static constexpr int kSmem = ATT_TILE_BYTES + kStages * kStageBytes + kBarBytes + kXchBytes + 1024;
+  static constexpr int kQBytes = kQT ? 0 : ATT_TILE_BYTES;
+  static constexpr int kSBase = kQT ? 256 : 128;                 // first TMEM column of the S buffers
+  static constexpr int kSmem = kQBytes + kStages * kStageBytes + kBarBytes + kXchBytes + 1024;
 };
 
 __device__ __forceinline__ void group_barrier(int id, int threads) {
   asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <int kSplit, int kMode, int kTrace = 0, int kPoly = 0>   // kPoly = n > 0: every n-th pair of exponentials of the plain tiles on the FMA pipe
-__global__ void __launch_bounds__(Att1<kSplit>::kThreads, 1)
+template <int kSplit, int kMode, int kTrace = 0, int kPoly = 0, bool kQT = false>   // kPoly = n > 0: every n-th pair of exponentials of the plain tiles on the FMA pipe
+__global__ void __launch_bounds__(Att1<kSplit, kQT>::kThreads, 1)
     k_attn_fwd1t(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  using C = Att1<kSplit>;
+  using C = Att1<kSplit, kQT>;
   constexpr int kStages = C::kStages;
+  constexpr int kBufs = C::kBufs;
+  constexpr uint32_t kSBase = C::kSBase;
   constexpr int kStageBytes = C::kStageBytes;
   constexpr int kPartBytes = C::kPartBytes;
   constexpr int kKvHalf = kPartBytes / 2;
@@ -1396,7 +1408,7 @@ __global__ void __launch_bounds__(Att1<kSplit>::kThreads, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* smem_q = smem;                        // [2 halves][128 x 128 B]
-  uint8_t* smem_kv = smem + ATT_TILE_BYTES;      // [stages]{K part [2 halves][64 x 128 B], V^T part [2 halves][64 x 128 B]}
+  uint8_t* smem_kv = smem + C::kQBytes;          // [stages]{K part [2 halves][64 x 128 B], V^T part [2 halves][64 x 128 B]}
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_kv + kStages * kStageBytes);
   uint64_t* q_full = bars;                        // [1]
   uint64_t* st_full = bars + 1;                   // [stages]
@@ -1419,7 +1431,7 @@ __global__ void __launch_bounds__(Att1<kSplit>::kThreads, 1)
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 2);
+    mbar_init(q_full, kQT ? 2 * C::kSoftmaxWarps : 2);   // kQT: one arrive per softmax warp of the pair (Q stored to TMEM)
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&st_full[i], 2);
       mbar_init(&st_empty[i], 1);
@@ -1448,7 +1460,7 @@ __global__ void __launch_bounds__(Att1<kSplit>::kThreads, 1)
   if (warp == kLoader) {
     if (lane == 0) {
       // ===== TMA producer: Q once, then K_0 K_1 K_2, V_0 K_3, V_1 K_4, ... (the issuer's consumption order) =====
-      if (pass == 0) {
+      if (!kQT && pass == 0) {
         if (crank == 0) mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);  // both CTAs' Q tiles
         else mbar_arrive_leader(q_full);
 #pragma unroll
@@ -1457,10 +1469,15 @@ __global__ void __launch_bounds__(Att1<kSplit>::kThreads, 1)
       }
       const int tiles_per_chunk = p.vt_chunk_len / ATT_TILE;
       const int n_chunks = p.Lk / p.vt_chunk_len;
+      // The order of the KV tiles is free (softmax sums commute).  All CTAs of a wave start together and advance at the
+      // same pace: visiting the tiles in the same order makes all 148 SMs request the same 64 KB of K / V within the same
+      // microsecond.  Each CTA pair therefore starts at its own offset inside every chunk (kv_rotate).
+      const int rot = p.kv_rotate ? (int)(((blockIdx.x >> 1) * 37u + blockIdx.y * 11u) % (unsigned)tiles_per_chunk) : 0;
       auto locate = [&](int j, int& chunk, int& within) {
         chunk = p.first_chunk + j / tiles_per_chunk;
         if (chunk >= n_chunks) chunk -= n_chunks;
-        within = j % tiles_per_chunk;
+        within = j % tiles_per_chunk + rot;
+        if (within >= tiles_per_chunk) within -= tiles_per_chunk;
       };
       // one ring stage = {K_jk, V_jv} (either may be absent: -1); ONE full / empty barrier pair per stage, so that the
       // issuer spends one wait and one commit per KV step on the ring
@@ -1474,7 +1491,7 @@ __global__ void __launch_bounds__(Att1<kSplit>::kThreads, 1)
         if (jk >= 0) {
           int chunk, within;
           locate(jk, chunk, within);
-          if (p.chunk_flags && within == 0 && chunk != p.first_chunk) {  // a remote chunk: wait for its producer rank
+          if (p.chunk_flags && jk % tiles_per_chunk == 0 && chunk != p.first_chunk) {  // first visit of a remote chunk: wait for its producer rank
             uint32_t v, spins = 0;
             uint64_t t0 = 0;
             for (;;) {
@@ -1503,8 +1520,8 @@ __global__ void __launch_bounds__(Att1<kSplit>::kThreads, 1)
         }
         if (++slot == kStages) { slot = 0; phase ^= 1; }
       };
-      for (int j = 0; j < 3 && j < n_kv; ++j) fill(j, -1);
-      for (int j = 0; j < n_kv; ++j) fill(j + 3 < n_kv ? j + 3 : -1, j);
+      for (int j = 0; j < kBufs && j < n_kv; ++j) fill(j, -1);
+      for (int j = 0; j < n_kv; ++j) fill(j + kBufs < n_kv ? j + kBufs : -1, j);
     }
   } else if (warp == kIssuer) {
     if (crank == 0) {
@@ -1519,9 +1536,13 @@ __global__ void __launch_bounds__(Att1<kSplit>::kThreads, 1)
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const uint32_t half = k >> 2, off = (k & 3) * 32;
-          uint64_t da = make_sdesc_sw128(smem_u32(smem_q + half * ATT_HALF_BYTES));
           uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + st * kStageBytes + half * kKvHalf));
-          if (issuer) umma_ss_2sm(tbase + 128 + b * 128, sdesc_advance(da, off), sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
+          if constexpr (kQT) {   // A = Q from TMEM: 16 head dimensions = 8 packed columns per k-step
+            if (issuer) umma_ts_2sm(tbase + kSBase + b * 128, tbase + 128 + k * 8, sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
+          } else {
+            uint64_t da = make_sdesc_sw128(smem_u32(smem_q + half * ATT_HALF_BYTES));
+            if (issuer) umma_ss_2sm(tbase + kSBase + b * 128, sdesc_advance(da, off), sdesc_advance(db, off), idesc, k != 0 ? 1u : 0u);
+          }
         }
       };
       auto mma_pv = [&](uint32_t b, uint32_t st, bool first) {   // O += P V : 8 k-steps of 16 keys; P quarter q at column 32 q
@@ -1530,12 +1551,12 @@ __global__ void __launch_bounds__(Att1<kSplit>::kThreads, 1)
           const uint32_t half = k >> 2, off = (k & 3) * 32;
           uint64_t db = make_sdesc_sw128(smem_u32(smem_kv + st * kStageBytes + kPartBytes + half * kKvHalf));
           if (issuer)
-            umma_ts_2sm(tO, tbase + 128 + b * 128 + (k >> 1) * 32 + (k & 1) * 8, sdesc_advance(db, off), idesc,
+            umma_ts_2sm(tO, tbase + kSBase + b * 128 + (k >> 1) * 32 + (k & 1) * 8, sdesc_advance(db, off), idesc,
                         (first && k == 0) ? 0u : 1u);
         }
       };
       if (pass == 0) mbar_wait_ns(q_full, 0, p.peer_timeout_ns);
-      for (int j = 0; j < 3 && j < n_kv; ++j) {
+      for (int j = 0; j < kBufs && j < n_kv; ++j) {
         mbar_wait_ns(&st_full[slot], phase, p.peer_timeout_ns);  // K_j
         tc_fence_after();
         mma_s((uint32_t)j, slot);
@@ -1557,13 +1578,13 @@ __global__ void __launch_bounds__(Att1<kSplit>::kThreads, 1)
         tc_fence_after();
         mma_pv(b, slot, j == 0);
         ATT_TR(0, 3);
-        if (j + 3 < n_kv) mma_s(b, slot);
+        if (j + kBufs < n_kv) mma_s(b, slot);
         ATT_TR(0, 4);
         commit(&s_full[b]);     // S(j+3) ready / P.V(j) complete (consumed by a rescale of step j+1 and by the epilogue)
         commit(&st_empty[slot]);
         ATT_TR(0, 5);
         advance();
-        b = b == 2 ? 0 : b + 1;
+        b = b == kBufs - 1 ? 0 : b + 1;
       }
     }
   } else {
@@ -1571,7 +1592,7 @@ __global__ void __launch_bounds__(Att1<kSplit>::kThreads, 1)
     const int h = warp >> 2, quad = warp & 3;
     const uint32_t lane_base = ((uint32_t)quad * 32u) << 16;
     const int rowl = quad * 32 + (int)lane;
-    const uint32_t tSw = tmem_base + lane_base + 128 + h * kKeys;     // + 128 b: this thread's S columns (P: same base)
+    const uint32_t tSw = tmem_base + lane_base + kSBase + h * kKeys;  // + 128 b: this thread's S columns (P: same base)
     const uint32_t tO = tmem_base + lane_base + h * kKeys;            // its O columns
     const int group_id = 1 + quad;
     const float c = p.scale_log2;
@@ -1597,7 +1618,7 @@ __global__ void __launch_bounds__(Att1<kSplit>::kThreads, 1)
     // s_full[(j-1) % 3], waited for without consuming it.  The warps of the quadrant then synchronise: P.V(j) updates
     // all 128 columns of O, so none may release P before all have rescaled.
     auto rescale = [&](float alpha, uint32_t b) {
-      const uint32_t bp = b == 0 ? 2u : b - 1u;
+      const uint32_t bp = b == 0 ? (uint32_t)(kBufs - 1) : b - 1u;
       mbar_wait_ns(&s_full[bp], (sph >> bp) & 1u, p.peer_timeout_ns);
       tc_fence_after();
       l *= alpha;
@@ -1699,21 +1720,46 @@ __global__ void __launch_bounds__(Att1<kSplit>::kThreads, 1)
       l += tsum;
       bad |= !(tsum < 1.0995116e12f /* 2^40 */);
     };
+    if constexpr (kQT) {
+      if (pass == 0) {
+        // this thread's share of its Q row -> TMEM (bf16 pairs per column: the K-major A operand layout of the S MMA)
+        uint32_t qv[kKeys / 2];
+        const int qrow = q0 + rowl;
+        if (qrow < p.Lq) {
+          const uint4* src = reinterpret_cast<const uint4*>(p.Q + (size_t)qrow * p.ldq + head * 128 + h * kKeys);
+#pragma unroll
+          for (int i = 0; i < kKeys / 8; ++i) {
+            const uint4 v = __ldg(src + i);
+            qv[4 * i + 0] = v.x; qv[4 * i + 1] = v.y; qv[4 * i + 2] = v.z; qv[4 * i + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < kKeys / 2; ++i) qv[i] = 0u;
+        }
+        const uint32_t tQw = tmem_base + lane_base + 128 + h * (kKeys / 2);
+        if constexpr (kKeys == 32) tmem_st16(tQw, qv);
+        else tmem_st32(tQw, qv);
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(q_full);
+      }
+    }
     {
       uint32_t b = 0;
       if (exact) {
 #pragma unroll 1
-        for (int j = 0; j < n_kv; ++j) { tile_exact(j, b); b = b == 2 ? 0 : b + 1; }
+        for (int j = 0; j < n_kv; ++j) { tile_exact(j, b); b = b == kBufs - 1 ? 0 : b + 1; }
       } else {
         tile_exact(0, 0);
         b = 1;
 #pragma unroll 1
-        for (int j = 1; j < n_kv; ++j) { tile_fast(b, j); b = b == 2 ? 0 : b + 1; }
+        for (int j = 1; j < n_kv; ++j) { tile_fast(b, j); b = b == kBufs - 1 ? 0 : b + 1; }
       }
     }
     // the issuer commits s_full behind every P.V: consume the completions of the last (up to three) steps; the last one
     // says that O is final
-    for (int j = n_kv > 3 ? n_kv - 3 : 0; j < n_kv; ++j) wait_s((uint32_t)(j % 3));
+    for (int j = n_kv > kBufs ? n_kv - kBufs : 0; j < n_kv; ++j) wait_s((uint32_t)(j % kBufs));
     xsum[h * 128 + rowl] = l;
     group_barrier(group_id, 32 * kSplit);
     float lt = l;
@@ -1803,7 +1849,7 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
   }
   // G3C_ATTN_MODE: softmax variant (see k_attn_fwd), 2 = sum-guarded reference (default), 0 = exact max per tile;
   // G3C_ATTN_POLY=4: every 4th exponential on the FMA pipe (measured slower, kept for A/B runs)
-  static int poly = -1, mode = 2, cluster = 1, two_cta = 1, shared_s = 1, w16 = 0, one_tile = 4, poly1t = 4, short_1t = 0;
+  static int poly = -1, mode = 2, cluster = 1, two_cta = 1, shared_s = 1, w16 = 0, one_tile = 4, poly1t = 4, short_1t = 0, q_tmem = 0;
   if (poly < 0) {
     const char* e = getenv("G3C_ATTN_POLY");
     poly = e ? atoi(e) : G3C_ATTN_POLY_DEFAULT;
@@ -1823,6 +1869,10 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     if (one_tile != 0 && one_tile != 2 && one_tile != 4) one_tile = 4;
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd1t<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att1<2>::kSmem));
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd1t<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att1<4>::kSmem));
+    e = getenv("G3C_ATTN_QT");       // 1: Q in TMEM, two S buffers, six ring stages (k_attn_fwd1t<.., kQT>)
+    q_tmem = e ? atoi(e) != 0 : 0;
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd1t<4, 2, 0, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att1<4, true>::kSmem));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd1t<4, 2, 1, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att1<4, true>::kSmem));
     e = getenv("G3C_ATTN_SHORT1T");  // 1: short key ranges (cross-attention) on the pipelined kernel too
     short_1t = e ? atoi(e) != 0 : 0;
     e = getenv("G3C_ATTN_POLY1T");   // 2 | 3 | 4: every n-th pair of exponentials on the FMA pipe (k_attn_fwd1t<4>)
@@ -1831,7 +1881,7 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd1t<4, 2, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att1<4>::kSmem));
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd1t<4, 2, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att1<4>::kSmem));
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd1t<2, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att1<2>::kSmem));
-    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd1t<4, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att1<4>::kSmem));
+    G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd1t<4, 2, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Att1<4>::kSmem));
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd16<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT16_SMEM));
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd16<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT16_SMEM));
     G3C_CUDA(cudaFuncSetAttribute(k_attn_fwd16<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT16_SMEM));
@@ -1857,6 +1907,8 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
   p.ldo = ldo;
   p.vt_chunk_len = vt_chunk_len;
   p.O = reinterpret_cast<__nv_bfloat16*>(o);
+  p.Q = reinterpret_cast<const __nv_bfloat16*>(q);
+  p.ldq = ldq;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.unit_scale = fabsf(p.scale_log2 - 1.0f) < 1e-6f;  // scale = ln 2: the caller already folded scale * log2(e) into Q
   if (p.unit_scale) p.scale_log2 = 1.0f;
@@ -1897,6 +1949,12 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
     dup_loads = e ? atoi(e) : 0;
   }
   p.dbg_dup_loads = dup_loads;
+  static int kv_rotate = -1;
+  if (kv_rotate < 0) {
+    const char* e = getenv("G3C_ATTN_ROTATE");
+    kv_rotate = e ? atoi(e) != 0 : 0;   // measured: no effect on the step (2 596-2 613 ms of self-attention either way)
+  }
+  p.kv_rotate = kv_rotate;
   p.trace = g_attn_trace;
   const char* tmo = getenv("G3C_ATTN_TRACE_MMA_ONLY");
   const int trace_level = g_attn_trace ? ((tmo && atoi(tmo)) ? 2 : 1) : 0;
@@ -1948,15 +2006,24 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
       }
       if (one_tile && trace_level && !p.split_s && !shared_s) {
         cfg.gridDim = dim3((((unsigned)(Lq + ATT_TILE - 1) / ATT_TILE) + 1) & ~1u, grid.y);
-        if (one_tile == 4) {
+        if (one_tile == 4 && q_tmem) {
+          cfg.blockDim = dim3(Att1<4, true>::kThreads);
+          cfg.dynamicSmemBytes = Att1<4, true>::kSmem;
+          G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd1t<4, 2, 1, 4, true>, tmQ, tmK2, tmV2, p));
+        } else if (one_tile == 4) {
           cfg.blockDim = dim3(Att1<4>::kThreads);
           cfg.dynamicSmemBytes = Att1<4>::kSmem;
-          G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd1t<4, 2, 1>, tmQ, tmK2, tmV2, p));
+          G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd1t<4, 2, 1, 4>, tmQ, tmK2, tmV2, p));
         } else {
           cfg.blockDim = dim3(Att1<2>::kThreads);
           cfg.dynamicSmemBytes = Att1<2>::kSmem;
           G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd1t<2, 2, 1>, tmQ, tmK2, tmV2, p));
         }
+      } else if (one_tile == 4 && q_tmem && !p.split_s && !shared_s && (reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+        cfg.gridDim = dim3((((unsigned)(Lq + ATT_TILE - 1) / ATT_TILE) + 1) & ~1u, grid.y);
+        cfg.blockDim = dim3(Att1<4, true>::kThreads);
+        cfg.dynamicSmemBytes = Att1<4, true>::kSmem;
+        G3C_CUDA(cudaLaunchKernelEx(&cfg, k_attn_fwd1t<4, 2, 0, 4, true>, tmQ, tmK2, tmV2, p));
       } else if (one_tile == 4 && poly1t && !p.split_s && !shared_s) {
         cfg.gridDim = dim3((((unsigned)(Lq + ATT_TILE - 1) / ATT_TILE) + 1) & ~1u, grid.y);
         cfg.blockDim = dim3(Att1<4>::kThreads);

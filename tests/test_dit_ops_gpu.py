@@ -103,8 +103,13 @@ def sdpa_ref(q, k, v, heads):
     return o.permute(1, 0, 2).reshape(Lq, D)
 
 
+# Lk > 1024 runs the pipelined kernel (one query tile per CTA pair half, three S buffers): cover n_kv mod 3 in {0, 1, 2},
+# ragged Lq (rows of the last tile and whole padding CTAs masked at the store), an odd number of query tiles, and a
+# chunked V^T layout (the context-parallel K/V order)
 @pytest.mark.parametrize("Lq,Lk,heads,chunks", [(256, 128, 1, 1), (256, 512, 2, 1), (384, 1024, 2, 1),
-                                                  (1280, 2560, 4, 1), (512, 1024, 2, 2), (7040, 7040, 2, 1)])
+                                                  (1280, 2560, 4, 1), (512, 1024, 2, 2), (7040, 7040, 2, 1),
+                                                  (300, 1152, 1, 1), (200, 1280, 2, 1), (130, 1408, 1, 1),
+                                                  (640, 2048, 2, 2), (896, 3072, 1, 3)])
 def test_attention(Lq, Lk, heads, chunks):
     from gen3c_b200 import ops
 

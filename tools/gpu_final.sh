@@ -12,5 +12,6 @@ TO=300 TAILN=4 run ncu_attn ncu --set full --clock-control none --import-source 
 TO=300 TAILN=4 run ncu_attn_cp8 ncu --set full --clock-control none --import-source on -k regex:k_attn_fwd -s 1 -c 1 -o gpurun_out/${TAG}_attn_cp8 -f python tools/ncu_target.py attn_cp8
 TO=300 TAILN=4 run ncu_gemm ncu --set full --clock-control none --import-source on -k regex:k_gemm -s 2 -c 2 -o gpurun_out/${TAG}_gemm -f python tools/ncu_target.py gemm
 TO=300 TAILN=4 run ncu_warp ncu --set full --clock-control none --import-source on -k regex:"k_splat|k_normalise|k_project" -s 4 -c 3 -o gpurun_out/${TAG}_splat -f python tools/ncu_target.py warp
+TO=120 TAILN=8 run ${TAG}_attn_trace_1t python tools/attn_trace1t.py
 # launch list of the whole bench process, Path D step + extras + Path R leg (cold-cache, serialised: compare SHARES)
 TO=600 TAILN=3 run ncu_list ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras
