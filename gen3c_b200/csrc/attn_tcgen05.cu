@@ -67,8 +67,9 @@ struct AttnParams {
                               // exponentials and before P.V(j), which shortens the per-tile dependent chain by half an S MMA
   const __nv_bfloat16* Q;     // k_attn_fwd1t<kQT>: Q rows are read straight from global memory into TMEM
   int ldq;
+  int big_boxes;              // k_attn_fwd1t: K / V^T parts arrive as ONE 16 KB TMA box each (tensor maps with the 64-element halves as an extra dimension)
   int kv_rotate;              // k_attn_fwd1t: every CTA pair visits the KV tiles of a chunk from its own start offset
-  int dbg_dup_loads;          // experiment (G3C_ATTN_DUP_LOADS): k_attn_fwd1t fetches every K / V part this many extra times
+  int dbg_dup_loads;          // unused (round-2 experiment: every K / V part fetched twice cost +9 % of the step, three times +23 %)
   unsigned long long* trace;  // kTrace only: [3 roles][64 steps][8 slots] clock64 stamps of CTA (0,0)
 };
 
@@ -1458,70 +1459,76 @@ __global__ void __launch_bounds__(Att1<kSplit, kQT>::kThreads, 1)
   for (;;) {
   const bool exact = kMode != 2 || pass == 1;
   if (warp == kLoader) {
-    if (lane == 0) {
-      // ===== TMA producer: Q once, then K_0 K_1 K_2, V_0 K_3, V_1 K_4, ... (the issuer's consumption order) =====
+    {
+      // ===== TMA producer: Q once, then K_0 .. K_{kBufs-1}, then {V_j, K_{j+kBufs}} per step (the issuer's consumption order).
+      // The whole warp runs this loop converged and ONE elected lane executes the TMA / mbarrier instructions: inside an
+      // `if (lane == 0)` region every UTMALDG operand is lane-varying for ptxas, and each load became an ELECT + 5 x
+      // R2UR.BROADCAST loop — together with integer divisions on the (exponential-saturated) XU pipe this thread needed
+      // ~1 300 clk per ring stage and paced the whole kernel (clock64 trace, profiles/r02_attn_trace_1t.txt) =====
+      const bool issuer = elect_one();
       if (!kQT && pass == 0) {
-        if (crank == 0) mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);  // both CTAs' Q tiles
-        else mbar_arrive_leader(q_full);
+        if (issuer) {
+          if (crank == 0) mbar_expect_tx(q_full, 2 * ATT_TILE_BYTES);  // both CTAs' Q tiles
+          else mbar_arrive_leader(q_full);
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-          tma_load_2d_2sm(smem_q + h * ATT_HALF_BYTES, &tmQ, q_full, head * 128 + h * 64, q0);
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d_2sm(smem_q + h * ATT_HALF_BYTES, &tmQ, q_full, head * 128 + h * 64, q0);
+        }
       }
       const int tiles_per_chunk = p.vt_chunk_len / ATT_TILE;
       const int n_chunks = p.Lk / p.vt_chunk_len;
-      // The order of the KV tiles is free (softmax sums commute).  All CTAs of a wave start together and advance at the
-      // same pace: visiting the tiles in the same order makes all 148 SMs request the same 64 KB of K / V within the same
-      // microsecond.  Each CTA pair therefore starts at its own offset inside every chunk (kv_rotate).
+      // The order of the KV tiles inside a chunk is free (softmax sums commute): kv_rotate starts every CTA pair at its own
+      // offset (measured: no effect; off by default).
       const int rot = p.kv_rotate ? (int)(((blockIdx.x >> 1) * 37u + blockIdx.y * 11u) % (unsigned)tiles_per_chunk) : 0;
-      auto locate = [&](int j, int& chunk, int& within) {
-        chunk = p.first_chunk + j / tiles_per_chunk;
-        if (chunk >= n_chunks) chunk -= n_chunks;
-        within = j % tiles_per_chunk + rot;
-        if (within >= tiles_per_chunk) within -= tiles_per_chunk;
-      };
-      // one ring stage = {K_jk, V_jv} (either may be absent: -1); ONE full / empty barrier pair per stage, so that the
-      // issuer spends one wait and one commit per KV step on the ring
-      auto fill = [&](int jk, int jv) {
+      // Two cursors (K stream, V stream) advanced tile by tile: no integer division in this loop (I2F / MUFU.RCP / F2I
+      // queue behind the exponentials on the XU pipe).
+      int k_chunk = p.first_chunk, k_within = 0, v_chunk = p.first_chunk, v_within = 0;
+      auto fill = [&](bool has_k, bool has_v, int j) {
+        if (crank == 0) ATT_TR(1, 4);
         mbar_wait_ns(&st_empty[slot], phase ^ 1, p.peer_timeout_ns);
-        const uint32_t parts = (jk >= 0 ? 1u : 0u) + (jv >= 0 ? 1u : 0u);
-        const int reps = 1 + p.dbg_dup_loads;
-        if (crank == 0) mbar_expect_tx(&st_full[slot], reps * parts * 2 * kPartBytes);   // both CTAs' halves
-        else mbar_arrive_leader(&st_full[slot]);
+        if (crank == 0) ATT_TR(1, 5);
         uint8_t* st = smem_kv + slot * kStageBytes;
-        if (jk >= 0) {
-          int chunk, within;
-          locate(jk, chunk, within);
-          if (p.chunk_flags && jk % tiles_per_chunk == 0 && chunk != p.first_chunk) {  // first visit of a remote chunk: wait for its producer rank
+        if (issuer) {
+          const uint32_t parts = (has_k ? 1u : 0u) + (has_v ? 1u : 0u);
+          if (crank == 0) mbar_expect_tx(&st_full[slot], parts * 2 * kPartBytes);   // both CTAs' halves
+          else mbar_arrive_leader(&st_full[slot]);
+        }
+        if (has_k) {
+          const int chunk = k_chunk;
+          int within = k_within + rot;
+          if (within >= tiles_per_chunk) within -= tiles_per_chunk;
+          const bool first_of_chunk = k_within == 0;
+          if (++k_within == tiles_per_chunk) { k_within = 0; if (++k_chunk == n_chunks) k_chunk = 0; }
+          if (p.chunk_flags && first_of_chunk && chunk != p.first_chunk) {  // first visit of a remote chunk: wait for its producer rank
             uint32_t v, spins = 0;
             uint64_t t0 = 0;
             for (;;) {
               asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p.chunk_flags + chunk) : "memory");
-              if ((int)(v - p.flag_seq) >= 0) break;
+              if (__all_sync(0xffffffffu, (int)(v - p.flag_seq) >= 0)) break;
               if (t0 == 0) t0 = global_timer_ns();
               if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > p.peer_timeout_ns) asm volatile("trap;\n");
             }
-            if (t0 != 0 && p.wait_ns) atomicAdd(p.wait_ns, (unsigned long long)(global_timer_ns() - t0));
+            if (issuer && t0 != 0 && p.wait_ns) atomicAdd(p.wait_ns, (unsigned long long)(global_timer_ns() - t0));
             asm volatile("fence.proxy.async.global;\n" ::: "memory");
           }
           const int kv0 = chunk * p.vt_chunk_len + within * ATT_TILE;
-          for (int r = 0; r < reps; ++r)
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-              tma_load_2d_2sm(st + h * kKvHalf, &tmK, &st_full[slot], head * 128 + h * 64, kv0 + (int)crank * 64);
+          // one 16 KB box {64 head dimensions, 64 keys, 2 halves}: shared memory [half][key][128 B]
+          if (issuer) tma_load_3d_2sm(st, &tmK, &st_full[slot], 0, kv0 + (int)crank * 64, head * 2);
         }
-        if (jv >= 0) {   // V_jv's chunk flag was checked when K_jv was loaded (three stages earlier)
-          int chunk, within;
-          locate(jv, chunk, within);
-          for (int r = 0; r < reps; ++r)
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-              tma_load_3d_2sm(st + kPartBytes + h * kKvHalf, &tmV, &st_full[slot], within * ATT_TILE + h * 64,
-                              head * 128 + (int)crank * 64, chunk);
+        if (has_v) {   // V_j's chunk flag was checked when K_j was loaded (kBufs stages earlier)
+          const int chunk = v_chunk;
+          int within = v_within + rot;
+          if (within >= tiles_per_chunk) within -= tiles_per_chunk;
+          if (++v_within == tiles_per_chunk) { v_within = 0; if (++v_chunk == n_chunks) v_chunk = 0; }
+          // one 16 KB box {64 keys, 64 head dimensions, 2 key halves, 1 chunk}
+          if (issuer)
+            tma_load_4d_2sm(st + kPartBytes, &tmV, &st_full[slot], 0, head * 128 + (int)crank * 64, within * 2, chunk);
         }
+        if (crank == 0) ATT_TR(1, 6);
         if (++slot == kStages) { slot = 0; phase ^= 1; }
       };
-      for (int j = 0; j < kBufs && j < n_kv; ++j) fill(j, -1);
-      for (int j = 0; j < n_kv; ++j) fill(j + kBufs < n_kv ? j + kBufs : -1, j);
+      for (int j = 0; j < kBufs && j < n_kv; ++j) fill(true, false, 63);
+      for (int j = 0; j < n_kv; ++j) fill(j + kBufs < n_kv, true, j);
     }
   } else if (warp == kIssuer) {
     if (crank == 0) {
@@ -1943,12 +1950,7 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
   }
   p.p_quarters = quarters && halves;
   G3C_REQUIRE(p.first_chunk >= 0 && p.first_chunk < Lk / vt_chunk_len, "attn: first chunk %d out of range", p.first_chunk);
-  static int dup_loads = -1;
-  if (dup_loads < 0) {
-    const char* e = getenv("G3C_ATTN_DUP_LOADS");
-    dup_loads = e ? atoi(e) : 0;
-  }
-  p.dbg_dup_loads = dup_loads;
+  p.dbg_dup_loads = 0;
   static int kv_rotate = -1;
   if (kv_rotate < 0) {
     const char* e = getenv("G3C_ATTN_ROTATE");
@@ -2003,6 +2005,26 @@ int attn_fwd_v1(const void* q, const void* k, const void* vt, void* o, int Lq, i
         uint32_t box[3] = {64, 64, 1};
         int rc = make_tmap_bf16_sw128(&tmV2, vt, 3, dims, str, box);
         if (rc) return rc;
+      }
+      p.big_boxes = 0;
+      if (one_tile && !p.split_s && !shared_s) {
+        // K as {64 elements, Lk keys, 2 * heads halves of 64 head dimensions}: box {64, 64, 2} = both halves of 64 keys;
+        // V^T as {64 keys, heads * 128 rows, chunk_len / 64 key halves, chunks}: box {64, 64, 2, 1}
+        {
+          uint64_t dims[3] = {64, (uint64_t)Lk, (uint64_t)heads * 2}, str[2] = {(uint64_t)ldk * 2, 128};
+          uint32_t box[3] = {64, 64, 2};
+          int rc = make_tmap_bf16_sw128(&tmK2, k, 3, dims, str, box);
+          if (rc) return rc;
+        }
+        {
+          const int chunks = Lk / vt_chunk_len;
+          uint64_t dims[4] = {64, (uint64_t)heads * 128, (uint64_t)vt_chunk_len / 64, (uint64_t)chunks};
+          uint64_t str[3] = {(uint64_t)vt_chunk_len * 2, 128, (uint64_t)vt_chunk_len * 2 * heads * 128};
+          uint32_t box[4] = {64, 64, 2, 1};
+          int rc = make_tmap_bf16_sw128(&tmV2, vt, 4, dims, str, box);
+          if (rc) return rc;
+        }
+        p.big_boxes = 1;
       }
       if (one_tile && trace_level && !p.split_s && !shared_s) {
         cfg.gridDim = dim3((((unsigned)(Lq + ATT_TILE - 1) / ATT_TILE) + 1) & ~1u, grid.y);

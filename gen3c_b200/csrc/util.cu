@@ -48,7 +48,7 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uin
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     return G3C_ECUDA;
   }
-  if (rank < 2 || rank > 3) {
+  if (rank < 2 || rank > 4) {
     set_error("tensor map rank %d unsupported", rank);
     return G3C_EINVAL;
   }
@@ -56,9 +56,9 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, int rank, const uin
     set_error("TMA base pointer %p not 16-byte aligned", base);
     return G3C_EINVAL;
   }
-  cuuint64_t gdims[3];
-  cuuint64_t gstr[2];
-  cuuint32_t gbox[3], estr[3];
+  cuuint64_t gdims[4];
+  cuuint64_t gstr[3];
+  cuuint32_t gbox[4], estr[4];
   for (int i = 0; i < rank; ++i) {
     gdims[i] = dims[i];
     gbox[i] = box[i];

@@ -39,5 +39,6 @@ d = lambda r, a, b: float((t[r, sl, b] - t[r, sl, a]).mean())  # noqa: E731
 print(f"issuer: wait stage {d(0,0,1):.0f} | wait P {d(0,1,2):.0f} | issue P.V {d(0,2,3):.0f} | issue S {d(0,3,4):.0f} | commits {d(0,4,5):.0f}")
 for r in (1, 2):
     print(f"{names[r][0][:10]}: period {float((t[r, 9:57, 0] - t[r, 8:56, 0]).mean()):.0f} | wait S {d(r,0,1):.0f} | LDTM {d(r,1,2):.0f} | exp+store+release {d(r,2,3):.0f}")
+print(f"loader (stage of step j): waits for the free slot {d(1,4,5):.0f} | issues its TMA loads {d(1,5,6):.0f} | issue -> issuer sees the stage {float((t[0, sl, 1] - t[1, sl, 6]).mean()):.0f} | slot free -> consumed, in steps of the issuer {float((t[0, sl, 1] - t[1, sl, 5]).mean()) / float((t[0, 9:57, 0] - t[0, 8:56, 0]).mean()):.2f}")
 print(f"softmax step j ends -> issuer sees P(j): {float((t[0, sl, 2] - t[1, sl, 3]).mean()):.0f} (h=0) {float((t[0, sl, 2] - t[2, sl, 3]).mean()):.0f} (h=last)")
 print(f"S(j+3) issued -> softmax starts step j+3 (slack; negative = softmax waits): {float((t[1, 11:59, 1] - t[0, 8:56, 4]).mean()):.0f}")
