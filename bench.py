@@ -549,7 +549,7 @@ def run_ours(args):
                    "parallelism": par_name, "l2": "inputs larger than L2 (14.5 GB weights, 0.9 GB residual stream)"},
         "e2e": {"value": 1e3 / ms_e2e, "unit": "steps/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
         "gpu_launches": launches_per_step * args.steps,
-        "roofline": {"bound": "tensor", "kernel": "k_attn_fwd (self-attention)", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "tensor", "kernel": "k_attn_fwd1t (self-attention)", "achieved": achieved, "peak": peak,
                      "unit": "TFLOP/s", "frac": achieved / peak,
                      # DRAM bytes of one launch from the committed ncu --set full capture of this kernel at the cp = 1
                      # shape; not meaningful for the sharded shapes, hence null there
