@@ -1,6 +1,12 @@
-// Path D — non-causal multi-head attention forward, head_dim 128, on tcgen05 / TMEM: per-tile S buffers with P
-// aliasing S, A/B tile alternation.  (Variants that were built and measured slower — 64-key tiles with double-buffered
-// S, one shared S buffer with separate P columns, 16 softmax warps — are described in profiles/r01_attention_variants.txt.)
+// Path D — non-causal multi-head attention forward, head_dim 128, on tcgen05 / TMEM.
+// Three kernels live here, in the order they were written:
+//   k_attn_fwd     two query tiles per CTA, per-tile S buffers with P aliasing S, A/B tile alternation (round 1 / early
+//                  round 2; today: key ranges <= 1 024 in its exact 1-CTA form, and the A/B baseline G3C_ATTN_1T=0)
+//   k_attn_fwd16   the same with 16 softmax warps (measured: no gain)
+//   k_attn_fwd1t   DEFAULT for self-attention: one query tile per CTA, three S buffers, software-pipelined over KV steps
+//                  (description above its definition; 96 % tensor-pipe activity)
+// Variants built and measured slower: profiles/r01_attention_variants.txt, profiles/r02_attention_variants.txt.
+// The text below describes k_attn_fwd.
 //   O = softmax(Q K^T * scale) V        (reference: cosmos_predict1/diffusion/module/attention.py
 //   :282-297 `cal_attn` -> transformer_engine DotProductAttention(sbhd, no_mask, dropout 0);
 //   self-attention Lq = Lk = 56 320, cross-attention Lk = 512)
@@ -1356,8 +1362,9 @@ __global__ void __launch_bounds__(ATT16_THREADS, 1)
 // 2 x 1 024 clk of MMA work and 2 x 1 090 clk of MUFU work), and at any time only one tile's warps feed the MUFU pipe.
 // With one O accumulator (128 columns) three S buffers fit (384 columns): the softmax warps go from step to step
 // without waiting for any MMA in the steady state, the tensor pipe always has P.V(j-1) and S(j+2) queued, and the
-// step period tends to max(MUFU time, MMA time) of ONE tile.  The price is K / V traffic per query row (each CTA pair
-// now covers 256 rows instead of 512): 32 KB per CTA and step from L2, which ran at 12 % of its throughput before.
+// step period tends to max(MUFU time, MMA time) of ONE tile (measured: 1 028 clk for 1 024 clk of MMAs).  The price is
+// K / V traffic per query row (each CTA pair now covers 256 rows instead of 512): 32 KB per CTA and step from L2, which
+// runs at 25 % of its throughput (12 % before); a cluster of four would halve it but strands 16 of the 148 SMs.
 //
 // Softmax: kSplit warps per TMEM lane quadrant, each owning 128 / kSplit keys of its 32 rows (two warps per
 // sub-partition saturate the MUFU pipe, one does not: profiles/r01_issue_rates_microbench.txt).  P (bf16) of key quarter
